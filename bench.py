@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — oligo-frequency-vector throughput on B200 (BASELINE.json metric: Gbases/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic sequences.  Default workload is
+BASELINE.json configs[1]: 10 M x 150 bp reads, k=5 canonical, f32 normalised rows (512 columns).
+  value     : Gbases/s with inputs and outputs resident in HBM (device entry point of the C ABI)
+  e2e       : Gbases/s through the host-buffer C-ABI call (pinned host buffers, H2D + D2H inside)
+  roofline  : algorithmic bytes / device time of the step vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the oracle's restatement of the reference algorithm (C + OpenMP, all host cores) on a
+                 bounded sample of the same workload.  The reference itself is Rust and cannot be
+                 built in this image, so kind = "port".
+N > 1 (torchrun): every rank runs the same per-GPU workload on its own GPU (weak scaling, rows are
+independent so there is no collective on the data path); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (n, length spec, k, canonical, out dtype, norm)
+    "reads150_k5": dict(n=10_000_000, length=150, k=5, dtype="f32", norm=1, seed=20250001,
+                        desc="10M x 150bp short reads, k=5 canonical f32 normalised (BASELINE configs[1])"),
+    "reads10k_k7": dict(n=1_000_000, length=10_000, k=7, dtype="f32", norm=1, seed=20250002,
+                        desc="1M x 10kbp long reads, k=7 canonical f32 normalised (BASELINE configs[2])"),
+    "contigs_k4": dict(n=20_000, length="contigs", k=4, dtype="f32", norm=1, seed=20250003,
+                       desc="20k metagenome contigs 1-500kbp with N runs, k=4 (BASELINE configs[3])"),
+    "reads10k_k8": dict(n=100_000, length=10_000, k=8, dtype="u32", norm=0, seed=20250004,
+                        desc="100k x 10kbp, k=8 canonical u32 counts (BASELINE configs[4] i)"),
+    "reads100k_k10": dict(n=2_000, length=100_000, k=10, dtype="u32", norm=0, seed=20250005,
+                          desc="2k x 100kbp, k=10 canonical u32 counts, global-atomic path (configs[4] ii)"),
+}
+DT = {"u32": (0, np.uint32, 4), "f32": (1, np.float32, 4), "f64": (2, np.float64, 8)}
+
+
+def dim_of(k: int) -> int:
+    return 4 ** k // 2 if k % 2 else (4 ** k + 4 ** (k // 2)) // 2
+
+
+def make_workload(spec: dict, scale: float, device):
+    """Synthetic bases/offsets on the GPU (torch RNG, seeded).  Returns (bases u8, offsets i64) tensors."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(spec["seed"])
+    n = max(32, int(spec["n"] * scale))
+    letters = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    if spec["length"] == "contigs":
+        # log-uniform lengths in [1e3, 5e5]; per-contig GC in [0.3, 0.7]; N runs; sporadic IUPAC; soft-masking
+        u = torch.rand(n, generator=g, device=device, dtype=torch.float64)
+        lengths = torch.exp(u * (np.log(5e5) - np.log(1e3)) + np.log(1e3)).to(torch.int64)
+        offsets = torch.zeros(n + 1, dtype=torch.int64, device=device)
+        offsets[1:] = torch.cumsum(lengths, 0)
+        total = int(offsets[-1])
+        seq_id = torch.repeat_interleave(torch.arange(n, device=device), lengths)
+        gc = 0.3 + 0.4 * torch.rand(n, generator=g, device=device)
+        r = torch.rand(total, generator=g, device=device)
+        gcb = gc[seq_id]
+        is_gc = r < gcb
+        half = torch.rand(total, generator=g, device=device) < 0.5
+        code = torch.where(is_gc, torch.where(half, 1, 2), torch.where(half, 0, 3))
+        bases = letters[code]
+        del r, gcb, is_gc, half, code, seq_id
+        # N runs: Poisson(2) per contig, log-uniform length [1, 1e4]
+        nruns = torch.poisson(torch.full((n,), 2.0, device=device), generator=g).to(torch.int64)
+        rid = torch.repeat_interleave(torch.arange(n, device=device), nruns)
+        rl = torch.exp(torch.rand(len(rid), generator=g, device=device) * np.log(1e4)).to(torch.int64)
+        rs = offsets[rid] + (torch.rand(len(rid), generator=g, device=device, dtype=torch.float64)
+                             * lengths[rid].double()).to(torch.int64)
+        re_ = torch.minimum(rs + rl, offsets[rid + 1])
+        delta = torch.zeros(total + 1, dtype=torch.int32, device=device)
+        delta.index_add_(0, rs, torch.ones_like(rs, dtype=torch.int32))
+        delta.index_add_(0, re_, -torch.ones_like(re_, dtype=torch.int32))
+        inrun = torch.cumsum(delta[:-1], 0) > 0
+        bases[inrun] = ord("N")
+        del delta, inrun
+        iupac = torch.tensor(list(b"RYKMSW"), dtype=torch.uint8, device=device)
+        m = torch.rand(total, generator=g, device=device) < 1e-4
+        bases[m] = iupac[torch.randint(0, 6, (int(m.sum()),), generator=g, device=device)]
+        # 5 % soft-masked: lower-case stretches of 1 kbp blocks
+        blk = torch.rand((total + 1023) // 1024, generator=g, device=device) < 0.05
+        low = torch.repeat_interleave(blk, 1024)[:total]
+        bases = torch.where(low & (bases != ord("N")), bases | 0x20, bases)
+        return bases.contiguous(), offsets
+    L = int(spec["length"])
+    total = n * L
+    bases = torch.empty(total, dtype=torch.uint8, device=device)
+    step = 1 << 28
+    for a in range(0, total, step):
+        b = min(total, a + step)
+        bases[a:b] = letters[torch.randint(0, 4, (b - a,), generator=g, device=device)]
+    offsets = torch.arange(n + 1, dtype=torch.int64, device=device) * L
+    if L <= 1000:   # 1 % of reads get one N at a uniform position
+        pick = torch.nonzero(torch.rand(n, generator=g, device=device) < 0.01).flatten()
+        pos = torch.randint(0, L, (len(pick),), generator=g, device=device)
+        bases[pick * L + pos] = ord("N")
+    else:           # 0.1 % of positions N, in runs of geometric mean length 10
+        nrun = int(total * 0.001 / 10)
+        st = torch.randint(0, total, (nrun,), generator=g, device=device)
+        ln = torch.distributions.Geometric(torch.tensor(0.1, device=device)).sample((nrun,)).to(torch.int64) + 1
+        for j in range(int(ln.max())):
+            m = ln > j
+            bases[torch.clamp(st[m] + j, max=total - 1)] = ord("N")
+    return bases, offsets
+
+
+def algorithmic_bytes(total_bases: int, n: int, dim: int, esize: int) -> int:
+    """ASCII bases + offset index + one output element per column."""
+    return total_bases + (n + 1) * 8 + n * dim * esize
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(spec: dict, bases_h: np.ndarray, offsets_h: np.ndarray, budget_reads: int):
+    """Time the oracle's port of the reference path on a bounded prefix of the workload."""
+    from oracle import oracle as O
+    n = min(len(offsets_h) - 1, budget_reads)
+    offs = np.ascontiguousarray(offsets_h[: n + 1]).astype(np.uint64)
+    nb = int(offs[-1])
+    O.baseline_batch(bases_h[:nb], offs[: min(n, 1000) + 1], spec["k"], True, spec["norm"])  # warm
+    t0 = time.perf_counter()
+    _, used = O.baseline_batch(bases_h[:nb], offs, spec["k"], True, spec["norm"])
+    dt = time.perf_counter() - t0
+    return nb / dt / 1e9, used, n, dt
+
+
+def run_reference(args, spec, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; Rust reference not buildable here)."""
+    if rank != 0:
+        return
+    rng = np.random.default_rng(spec["seed"])
+    L = spec["length"] if spec["length"] != "contigs" else 80_000
+    # size the per-step sample for ~3 s of all-core CPU work
+    from oracle import oracle as O
+    cores = O.max_threads()
+    reads = max(64, int(min(spec["n"] * args.scale, 3.0 * cores * 0.25e9 / L)))
+    lengths = np.full(reads, L, dtype=np.uint64)
+    offsets = np.zeros(reads + 1, dtype=np.uint64)
+    np.cumsum(lengths, out=offsets[1:])
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(offsets[-1]), dtype=np.uint8)]
+    for _ in range(args.warmup):
+        O.baseline_batch(bases, offsets, spec["k"], True, spec["norm"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, used = O.baseline_batch(bases, offsets, spec["k"], True, spec["norm"])
+    dt = (time.perf_counter() - t0) / args.steps
+    val = int(offsets[-1]) / dt / 1e9
+    sample = f"{reads} sequences x {L} bp per step ({int(offsets[-1])} bases)"
+    line = {
+        "impl": "reference", "metric": "oligo_vectors_throughput", "value": val, "unit": "Gbases/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": spec["desc"], "k": spec["k"], "canonical": True},
+        "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": used, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sequences_per_s": reads / dt,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="reads150_k5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's sequence count")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--short-variant", type=int, default=None)
+    ap.add_argument("--force-path", type=int, default=None)
+    args = ap.parse_args()
+    spec = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, spec, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from kmertools_b200 import OligoComputer, HostBuffer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: kmertools_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    k = spec["k"]
+    code, npdt, esize = DT[spec["dtype"]]
+    dim = dim_of(k)
+    oc = OligoComputer(k, device=local)
+    if args.short_variant is not None:
+        oc.set_option("short_variant", args.short_variant)
+    if args.force_path is not None:
+        oc.set_option("force_path", args.force_path)
+    bases, offsets = make_workload(spec, args.scale, dev)
+    n = offsets.numel() - 1
+    total_bases = int(offsets[-1])
+    tdt = {"u32": torch.int32, "f32": torch.float32, "f64": torch.float64}[spec["dtype"]]
+    out = torch.empty((n, dim), dtype=tdt, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        oc.vectorise_device(bases.data_ptr(), offsets.data_ptr(), n, total_bases, out.data_ptr(),
+                            norm_mode=spec["norm"], mins=True, out_dtype=code, stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    launches_per_step = oc.stats()["launches"]
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # the timed region is long enough for several nvidia-smi samples: repeat the K-step block if needed
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    # keep the GPU under the same load a little longer so the clock sampler sees it (not timed)
+    t_end = time.time() + 1.0
+    while time.time() < t_end:
+        step()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * total_bases / (ms_per_step * 1e-3) / 1e9
+
+    # ---- sanity: size-independent property on the full output (rows sum to 1 or 0)
+    if spec["norm"]:
+        s = out[: min(n, 200_000)].sum(dim=1, dtype=torch.float64)
+        ok = bool(torch.all(((s - 1).abs() < 1e-3) | (s == 0)))
+    else:
+        ok = True
+
+    # ---- roofline of the step's dominant kernel
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    B = algorithmic_bytes(total_bases, n, dim, esize)
+    achieved = B / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": B,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    # ---- e2e through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        hb = HostBuffer((total_bases,), np.uint8)
+        ho = HostBuffer((n + 1,), np.uint64)
+        hout = HostBuffer((n, dim), npdt)
+        hb.array[:] = bases.cpu().numpy()
+        ho.array[:] = offsets.cpu().numpy().astype(np.uint64)
+        oc.vectorise_packed(hb.array, ho.array, norm_mode=spec["norm"], mins=True, dtype=npdt, out=hout.array)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            oc.vectorise_packed(hb.array, ho.array, norm_mode=spec["norm"], mins=True, dtype=npdt, out=hout.array)
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        st = oc.stats()
+        e2e = {"value": world * total_bases / dt / 1e9, "unit": "Gbases/s",
+               "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]),
+               "ms_per_step": dt * 1e3, "kernel_ms": st["kernel_ms"], "h2d_ms": st["h2d_ms"], "d2h_ms": st["d2h_ms"],
+               "host_memory": "pinned (ktb_host_alloc)"}
+        # parity spot check against the device-path result
+        same = bool(np.array_equal(hout.array[:1000], out[:1000].cpu().numpy()))
+        e2e["matches_device_path"] = same
+        keep_h = (hb, ho)
+        hout.free()
+    else:
+        keep_h = None
+
+    # ---- CPU baseline on rank 0 (bounded sample)
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        if keep_h is not None:
+            bh, oh = keep_h[0].array, keep_h[1].array
+        else:
+            bh, oh = bases.cpu().numpy(), offsets.cpu().numpy().astype(np.uint64)
+        from oracle import oracle as O
+        cores = O.max_threads()
+        mean_len = max(1, total_bases // n)
+        budget = max(64, int(cores * 0.15e9 * 4 / mean_len))   # ~4 s at ~0.15 Gbases/s/core
+        gb, used, ns, dt = cpu_sample(spec, bh, oh, budget)
+        cpu = {"value": gb, "unit": "Gbases/s", "cores": used, "kind": "port",
+               "sample": f"first {ns} sequences of the workload, {dt:.2f} s, C+OpenMP restatement of the reference "
+                         f"(Rust reference not buildable in this image)"}
+
+    if rank == 0:
+        line = {
+            "metric": "oligo_vectors_throughput", "value": value, "unit": "Gbases/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": spec["dtype"],
+            "data": "synthetic",
+            "config": {"workload": args.workload, "desc": spec["desc"], "k": k, "canonical": True, "dim": dim,
+                       "sequences_per_gpu": n, "bases_per_gpu": total_bases,
+                       "l2": "inputs+outputs per step exceed L2 (126 MB)" if B > 4 * 126e6 else "small working set"},
+            "sequences_per_s": world * n / (ms_per_step * 1e-3),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(launches_per_step * args.steps), "rows_sum_to_one": ok,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,141 @@
+/*
+ * kmertools_b200.h — C ABI of the B200-native oligonucleotide-frequency-vector path.
+ *
+ * This is the drop-in boundary for ONE hot path of anuradhawick/kmertools: per-sequence canonical
+ * (or raw) k-mer counting + L1 normalisation.  The reference has no FFI seam of its own (it is a
+ * single Rust process); the seam defined here is "batch of sequences -> dense row-major matrix",
+ * which is exactly what its three callers consume:
+ *
+ *   composition/src/oligo.rs:231-259   OligoComputer::vectorise_one   (CLI, norm_mode 0/1)
+ *   pybindings/src/oligo.rs:39-81      OligoComputer.vectorise_one / vectorise_batch (norm_mode 0/2)
+ *   composition/src/oligocgr.rs:145-163 OligoCgrComputer::seq_to_kmer (same histogram)
+ *
+ * Plain pointers and sizes only.  All entry points return KTB_OK (0) or an error code; the message
+ * is available from ktb_last_error() (thread-local).  Sequence CONTENT is never an error: ambiguous
+ * bytes reset the k-mer window exactly as kmer/src/kmer.rs:80-106 does.
+ *
+ * There is NO CPU fallback: every compute entry point fails with KTB_ERR_NODEVICE when no CUDA device
+ * is usable.
+ */
+#ifndef KMERTOOLS_B200_H
+#define KMERTOOLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KTB_ABI_VERSION 1
+
+/* status codes */
+#define KTB_OK 0
+#define KTB_ERR_ARG 1      /* bad argument (k out of range, NULL pointer, unknown enum) */
+#define KTB_ERR_CUDA 2     /* a CUDA call failed; see ktb_last_error() */
+#define KTB_ERR_NOMEM 3    /* host or device allocation failed */
+#define KTB_ERR_NODEVICE 4 /* no usable CUDA device */
+#define KTB_ERR_IO 5       /* file could not be opened / parsed / written */
+
+/* norm_mode: what vectorise_one does after counting.
+ *   COUNTS  no normalisation                                  (oligo.rs:255 with norm=false)
+ *   CLI     v[i] /= max(1, #kmers)                            (composition/src/oligo.rs:255-257)
+ *   PY      like CLI, but in raw (non-canonical) mode the divisor is 2*#kmers, reproducing
+ *           pybindings/src/oligo.rs:58-62 (`total += 2_f64`), so raw rows sum to 0.5 */
+#define KTB_NORM_COUNTS 0
+#define KTB_NORM_CLI 1
+#define KTB_NORM_PY 2
+
+/* out_dtype: element type of the output matrix.  U32 is only valid with KTB_NORM_COUNTS.
+ * F64 reproduces the reference's Vec<f64> bit for bit; F32 is (float)(that f64 value). */
+#define KTB_OUT_U32 0
+#define KTB_OUT_F32 1
+#define KTB_OUT_F64 2
+
+/* largest k the dense-vector path supports (4^12/2 columns = 33.5 MB per f32 row) */
+#define KTB_MAX_K 12
+
+typedef struct ktb_oligo ktb_oligo;
+
+/* Timings of the most recent vectorise call on a handle (milliseconds, CUDA events / host clock). */
+typedef struct ktb_stats {
+    double kernel_ms;      /* device time of the compute kernels (sum over chunks) */
+    double h2d_ms;         /* host->device copy time (host-buffer entry point only) */
+    double d2h_ms;         /* device->host copy time */
+    double wall_ms;        /* host wall clock of the whole call */
+    uint64_t launches;     /* kernels launched by this library during the call */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    uint64_t n_short;      /* sequences handled by the thread-per-read kernel */
+    uint64_t n_medium;     /* sequences handled by the CTA-per-sequence shared-memory kernel */
+    uint64_t n_long;       /* sequences split into tiles */
+    uint64_t n_global;     /* sequences counted with global-memory atomics (large k) */
+} ktb_stats;
+
+/* Number of CUDA devices visible to the library (0 when there is none / no driver). */
+int ktb_device_count(void);
+
+/* Replaces OligoComputer::new (composition/src/oligo.rs:31-47; pybindings/src/oligo.rs:22-31):
+ * builds the canonical-rank tables of KmerGenerator::kmer_pos_maps (kmer/src/kmer.rs:54-73) and
+ * uploads them to `device` (CUDA ordinal).  One handle per GPU; one process per GPU under torchrun.
+ * 1 <= k <= KTB_MAX_K. */
+int ktb_oligo_create(int k, int device, ktb_oligo **out);
+void ktb_oligo_destroy(ktb_oligo *h);
+
+int ktb_oligo_k(const ktb_oligo *h);
+/* Row width: canonical -> |{min(x, rc(x))}| (kmer.rs:54-73), raw -> 4^k (oligo.rs:232-236). */
+uint64_t ktb_oligo_dim(const ktb_oligo *h, int canonical);
+
+/* Replaces OligoComputer::get_header (composition/src/oligo.rs:69-83; pybindings/src/oligo.rs:85-99):
+ * dim labels of k characters each, written back to back (dim*k bytes, no separators, no NUL). */
+int ktb_oligo_header(const ktb_oligo *h, int canonical, char *buf, size_t cap);
+
+/* Replaces KmerGenerator::kmer_pos_maps (kmer/src/kmer.rs:54-73).  pos_map has 4^k entries
+ * (canonical code -> rank, 0 elsewhere), pos_to_kmer has dim(canonical) entries.  Either may be NULL. */
+int ktb_oligo_pos_maps(const ktb_oligo *h, uint64_t *pos_map, uint64_t *pos_to_kmer, uint64_t *count);
+
+/* Replaces OligoComputer::vectorise_one applied to a whole batch (pybindings vectorise_batch,
+ * pybindings/src/oligo.rs:77-81; the rayon map in composition/src/oligo.rs:126-143).
+ *
+ * HOST-buffer entry point.  `bases` holds the sequences back to back (ASCII or raw 0..3 codes, as the
+ * reference accepts), sequence i is bases[offsets[i] .. offsets[i+1]); offsets has n+1 entries.
+ * `out` is n x dim row-major of out_dtype, caller-owned host memory (pinned memory from
+ * ktb_host_alloc makes the copies asynchronous; pageable memory works too).  `totals` (optional, may
+ * be NULL) receives the number of valid k-mer windows per sequence.  The call chunks the batch,
+ * overlaps H2D / compute / D2H on CUDA streams and returns when `out` is complete. */
+int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offsets, uint64_t n,
+                        int canonical, int norm_mode, int out_dtype, void *out, uint64_t *totals);
+
+/* DEVICE-buffer entry point: same contract, but bases/offsets/out/totals are device pointers on the
+ * handle's GPU and the work is enqueued on `stream` (a cudaStream_t; NULL = default stream).
+ * Returns after enqueueing; results are ready when the stream reaches that point.
+ * out must be 16-byte aligned. */
+int ktb_oligo_vectorise_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets,
+                               uint64_t n, uint64_t total_bases, int canonical, int norm_mode,
+                               int out_dtype, void *d_out, uint64_t *d_totals, void *stream);
+
+/* Stats of the most recent vectorise call (host entry point: complete; device entry point: launch
+ * counts and class sizes only). */
+int ktb_oligo_last_stats(const ktb_oligo *h, ktb_stats *out);
+
+/* Tuning knobs (testing / benchmarking).  Known keys:
+ *   "chunk_bytes"   target bytes of output per pipeline chunk in the host entry point
+ *   "force_path"    0 auto, 1 global-atomic path only, 2 no thread-per-read kernel
+ *   "short_variant" 0 = byte read-modify-write histogram, 1 = packed shared-memory atomics */
+int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value);
+
+/* Pinned host memory for callers that want asynchronous copies. */
+void *ktb_host_alloc(size_t bytes);
+void ktb_host_free(void *p);
+
+/* Device byte -> 2-bit code table as the kernels compute it (256 entries); lets tests compare the
+ * in-kernel decoder with SEQ_NT4_TABLE (kmer/src/kmer.rs:6-15). */
+int ktb_debug_nt4_table(ktb_oligo *h, uint8_t *out256);
+
+const char *ktb_last_error(void);
+int ktb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMERTOOLS_B200_H */

@@ -1,0 +1,618 @@
+// api.cu — host side of the C ABI declared in include/kmertools_b200.h.
+//
+// Mirrors the reference's OligoComputer life cycle (composition/src/oligo.rs:31-93,
+// pybindings/src/oligo.rs:22-99): create = build the kmer_pos_maps tables once, vectorise = run the
+// per-sequence histogram + normalisation for a whole batch.  No CPU compute path exists here: without
+// a CUDA device every compute entry point returns KTB_ERR_NODEVICE.
+#include "../../include/kmertools_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? KTB_ERR_NOMEM : KTB_ERR_CUDA,            \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+uint64_t rev_comp(uint64_t x, int k) {  // kmer/src/kmer.rs:43-52
+    uint64_t r = 0;
+    for (int i = 0; i < k; ++i) {
+        r = (r << 2) | ((x & 3) ^ 3);
+        x >>= 2;
+    }
+    return r;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return KTB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(KTB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        cap = want;
+        return KTB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int NBUF = 3;
+
+struct ChunkSet {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};  // h2d start/end, kernel end, d2h end  (+2 spare)
+    DevBuf bases, offsets, out, totals;
+    bool busy = false;
+};
+
+}  // namespace
+
+struct ktb_oligo {
+    int k = 0;
+    int device = 0;
+    uint64_t ncodes = 0;  // 4^k
+    uint64_t dim_canon = 0;
+    std::vector<uint32_t> rank_of_canon;   // [4^k] canonical code -> rank, 0 elsewhere (pos_map)
+    std::vector<uint32_t> canon_of_rank;   // [dim_canon]
+    // device tables
+    uint32_t *d_rank_full = nullptr;       // [4^k] any code -> rank of its canonical form
+    uint32_t *d_canon_of_rank = nullptr;   // [dim_canon padded to 4]
+    uint16_t *d_short_tab_canon = nullptr; // [4^k] (k <= 5)
+    uint16_t *d_short_tab_raw = nullptr;
+    unsigned long long *d_counters = nullptr;  // [4]
+    DevBuf ws_totals, ws_counts;
+    ChunkSet sets[NBUF];
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    // options
+    int64_t chunk_bytes = 512ll << 20;
+    int force_path = 0;
+    int short_variant = 0;
+    int short_warps = 0;  // 0 = auto
+    ktb_stats stats{};
+};
+
+namespace {
+
+using namespace ktb;
+
+int set_device(const ktb_oligo *h) {
+    CU(cudaSetDevice(h->device));
+    return KTB_OK;
+}
+
+template <typename K>
+int set_smem(K kern, size_t bytes) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return KTB_OK;
+}
+
+struct ShortCfg {
+    bool ok = false;
+    uint32_t words = 0, stage_bytes = 0, max_len = 0;
+    int warps = 0;
+    size_t smem = 0;
+};
+
+ShortCfg short_config(const ktb_oligo *h, uint64_t dim) {
+    ShortCfg c;
+    if (h->ncodes > (uint64_t)SHORT_MAX_CODES || (dim & 3) || h->force_path != 0) return c;
+    c.words = (uint32_t)(dim / 4);
+    c.max_len = 254u + (uint32_t)h->k;
+    c.stage_bytes = ((32u * c.max_len + 16u + 15u) / 16u) * 16u;
+    if (c.stage_bytes < 32u * 33u * 4u) c.stage_bytes = 32u * 33u * 4u;
+    const size_t per_warp = (size_t)c.words * 128u + c.stage_bytes;
+    const size_t avail = h->smem_optin - 4096;  // static tables + slack
+    int warps = (int)(avail / per_warp);
+    if (warps > 16) warps = 16;
+    if (h->short_warps > 0 && h->short_warps < warps) warps = h->short_warps;
+    if (warps < 1) return c;
+    c.warps = warps;
+    c.smem = per_warp * (size_t)warps;
+    c.ok = true;
+    return c;
+}
+
+template <int OUT>
+int launch_short(ktb_oligo *h, const ShortParams &p, const ShortCfg &c, cudaStream_t st) {
+    auto kern = h->short_variant ? short_kernel<OUT, true> : short_kernel<OUT, false>;
+    if (int rc = set_smem(kern, c.smem)) return rc;
+    int per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, c.warps * 32, c.smem));
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)h->sm_count * per_sm;
+    const uint64_t need = (p.ngroups + c.warps - 1) / c.warps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, c.warps * 32, c.smem, st>>>(p);
+    CU(cudaGetLastError());
+    h->stats.launches++;
+    return KTB_OK;
+}
+
+template <int OUT>
+int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st) {
+    const size_t smem = (size_t)p.hist_entries * 4;
+    void (*kern)(const SeqParams) = nullptr;
+    if (hist_mode == 0) kern = seq_kernel<OUT, 0>;
+    else if (hist_mode == 1) kern = seq_kernel<OUT, 1>;
+    else kern = seq_kernel<OUT, 2>;
+    if (int rc = set_smem(kern, smem)) return rc;
+    int per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)h->sm_count * per_sm;
+    const uint64_t ngroups = (p.n + 31) / 32;
+    if (grid > ngroups) grid = ngroups;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 256, smem, st>>>(p);
+    CU(cudaGetLastError());
+    h->stats.launches++;
+    return KTB_OK;
+}
+
+template <int OUT>
+int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n,
+               uint64_t total_bases, int canonical, int norm_mode, void *d_out, uint64_t *d_totals,
+               cudaStream_t st) {
+    const uint64_t dim = canonical ? h->dim_canon : h->ncodes;
+    const size_t esize = (OUT == OUT_F64) ? 8 : 4;
+    if (n == 0) return KTB_OK;
+
+    // which histogram lives in shared memory?
+    const size_t smem_limit = h->smem_optin - 1024;
+    int hist_mode = -1;
+    uint64_t hist_entries = 0;
+    if (h->force_path != 1) {
+        if (!canonical) {
+            if (h->ncodes * 4 <= smem_limit) { hist_mode = 0; hist_entries = h->ncodes; }
+        } else if (h->ncodes * 4 <= 64 * 1024) {
+            hist_mode = 1; hist_entries = h->ncodes;
+        } else if (h->dim_canon * 4 <= smem_limit) {
+            hist_mode = 2; hist_entries = h->dim_canon;
+        }
+    }
+
+    if (hist_mode >= 0) {
+        CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
+        const ShortCfg sc = short_config(h, dim);
+        if (sc.ok) {
+            ShortParams sp{};
+            sp.bases = d_bases; sp.offsets = d_offsets; sp.n = n; sp.ngroups = (n + 31) / 32;
+            sp.out = d_out; sp.totals = d_totals;
+            sp.tab = canonical ? h->d_short_tab_canon : h->d_short_tab_raw;
+            sp.counter = h->d_counters + 0;
+            sp.k = h->k; sp.ncodes = (uint32_t)h->ncodes; sp.dim = (uint32_t)dim; sp.words = sc.words;
+            sp.stage_bytes = sc.stage_bytes; sp.max_len = sc.max_len;
+            sp.norm_mode = norm_mode; sp.canonical = canonical; sp.warps = sc.warps;
+            if (int rc = launch_short<OUT>(h, sp, sc, st)) return rc;
+        }
+        SeqParams qp{};
+        qp.bases = d_bases; qp.offsets = d_offsets; qp.n = n; qp.total_bases = total_bases;
+        qp.out = d_out; qp.totals = d_totals;
+        qp.rank_full = h->d_rank_full; qp.canon_of_rank = h->d_canon_of_rank;
+        qp.counter = h->d_counters + 1;
+        qp.k = h->k; qp.dim = (uint32_t)dim; qp.hist_entries = (uint32_t)hist_entries;
+        qp.norm_mode = norm_mode; qp.canonical = canonical;
+        qp.skip_short = sc.ok ? 1 : 0; qp.short_max_len = sc.max_len; qp.short_stage_bytes = sc.stage_bytes;
+        return launch_seq<OUT>(h, qp, hist_mode, st);
+    }
+
+    // ---- global-atomic path: zeroed u32 rows, flat decomposition, finalize
+    uint32_t *counts = nullptr;
+    if (OUT == OUT_F64) {
+        if (int rc = h->ws_counts.ensure(n * dim * 4)) return rc;
+        counts = (uint32_t *)h->ws_counts.p;
+    } else {
+        counts = (uint32_t *)d_out;
+    }
+    if (int rc = h->ws_totals.ensure(n * 8)) return rc;
+    unsigned long long *tot = (unsigned long long *)h->ws_totals.p;
+    CU(cudaMemsetAsync(counts, 0, n * dim * 4, st));
+    CU(cudaMemsetAsync(tot, 0, n * 8, st));
+    if (total_bases > 0) {
+        FlatParams fp{};
+        fp.bases = d_bases; fp.offsets = d_offsets; fp.n = n; fp.total_bases = total_bases;
+        fp.counts = counts; fp.totals = tot;
+        fp.rank_full = canonical ? h->d_rank_full : nullptr;
+        fp.dim = dim; fp.k = h->k;
+        const uint64_t nchunks = (total_bases + FLAT_CHUNK - 1) / FLAT_CHUNK;
+        uint64_t grid = (nchunks + 255) / 256;
+        const uint64_t cap = (uint64_t)h->sm_count * 32;
+        if (grid > cap) grid = cap;
+        flat_kernel<<<(unsigned)grid, 256, 0, st>>>(fp);
+        CU(cudaGetLastError());
+        h->stats.launches++;
+    }
+    if (OUT == OUT_U32) {
+        if (d_totals) CU(cudaMemcpyAsync(d_totals, tot, n * 8, cudaMemcpyDeviceToDevice, st));
+    } else {
+        uint64_t nel = n * dim;
+        uint64_t grid = (nel + 255) / 256;
+        const uint64_t cap = (uint64_t)h->sm_count * 16;
+        if (grid > cap) grid = cap;
+        finalize_kernel<OUT><<<(unsigned)grid, 256, 0, st>>>(counts, tot, d_out, d_totals, n, dim,
+                                                            norm_mode, canonical);
+        CU(cudaGetLastError());
+        h->stats.launches++;
+    }
+    (void)esize;
+    return KTB_OK;
+}
+
+int dispatch_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n,
+                    uint64_t total_bases, int canonical, int norm_mode, int out_dtype, void *d_out,
+                    uint64_t *d_totals, cudaStream_t st) {
+    switch (out_dtype) {
+        case KTB_OUT_U32:
+            return run_device<OUT_U32>(h, d_bases, d_offsets, n, total_bases, canonical, norm_mode, d_out, d_totals, st);
+        case KTB_OUT_F32:
+            return run_device<OUT_F32>(h, d_bases, d_offsets, n, total_bases, canonical, norm_mode, d_out, d_totals, st);
+        default:
+            return run_device<OUT_F64>(h, d_bases, d_offsets, n, total_bases, canonical, norm_mode, d_out, d_totals, st);
+    }
+}
+
+int check_args(const ktb_oligo *h, int canonical, int norm_mode, int out_dtype) {
+    if (!h) return fail(KTB_ERR_ARG, "null handle");
+    if (canonical != 0 && canonical != 1) return fail(KTB_ERR_ARG, "canonical must be 0 or 1");
+    if (norm_mode < 0 || norm_mode > 2) return fail(KTB_ERR_ARG, "unknown norm_mode %d", norm_mode);
+    if (out_dtype < 0 || out_dtype > 2) return fail(KTB_ERR_ARG, "unknown out_dtype %d", out_dtype);
+    if (out_dtype == KTB_OUT_U32 && norm_mode != KTB_NORM_COUNTS)
+        return fail(KTB_ERR_ARG, "KTB_OUT_U32 requires KTB_NORM_COUNTS");
+    return KTB_OK;
+}
+
+__global__ void rebase_offsets_kernel(uint64_t *offs, uint64_t count, uint64_t bias) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        offs[i] -= bias;
+}
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *ktb_last_error(void) { return g_err.c_str(); }
+int ktb_abi_version(void) { return KTB_ABI_VERSION; }
+
+int ktb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ktb_oligo_create(int k, int device, ktb_oligo **out) {
+    if (!out) return fail(KTB_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (k < 1 || k > KTB_MAX_K) return fail(KTB_ERR_ARG, "k must be in 1..%d (got %d)", KTB_MAX_K, k);
+    const int ndev = ktb_device_count();
+    if (ndev <= 0) return fail(KTB_ERR_NODEVICE, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(KTB_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+
+    ktb_oligo *h = new ktb_oligo();
+    h->k = k;
+    h->device = device;
+    h->ncodes = 1ULL << (2 * k);
+    // kmer_pos_maps (kmer/src/kmer.rs:54-73): canonical codes in ascending order get ranks 0..count-1.
+    // Walking x upward and keeping x when x <= rc(x) visits exactly the sorted canonical set.
+    h->rank_of_canon.assign(h->ncodes, 0);
+    std::vector<uint32_t> rank_full(h->ncodes);
+    for (uint64_t x = 0; x < h->ncodes; ++x) {
+        if (x <= rev_comp(x, k)) {
+            h->rank_of_canon[x] = (uint32_t)h->canon_of_rank.size();
+            h->canon_of_rank.push_back((uint32_t)x);
+        }
+    }
+    h->dim_canon = h->canon_of_rank.size();
+    for (uint64_t x = 0; x < h->ncodes; ++x) {
+        const uint64_t rc = rev_comp(x, k);
+        rank_full[x] = h->rank_of_canon[x < rc ? x : rc];
+    }
+
+    auto bail = [&](int rc) {
+        ktb_oligo_destroy(h);
+        return rc;
+    };
+    if (int rc = set_device(h)) return bail(rc);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return bail(fail(KTB_ERR_CUDA, "cudaGetDeviceProperties failed"));
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+
+#define CUB(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return bail(fail(KTB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)));       \
+    } while (0)
+
+    CUB(cudaMalloc(&h->d_rank_full, h->ncodes * 4));
+    CUB(cudaMemcpy(h->d_rank_full, rank_full.data(), h->ncodes * 4, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> cor(h->canon_of_rank);
+    while (cor.size() % 4) cor.push_back(0);
+    CUB(cudaMalloc(&h->d_canon_of_rank, cor.size() * 4));
+    CUB(cudaMemcpy(h->d_canon_of_rank, cor.data(), cor.size() * 4, cudaMemcpyHostToDevice));
+    if (h->ncodes <= (uint64_t)ktb::SHORT_MAX_CODES) {
+        std::vector<uint16_t> tc(h->ncodes), tr(h->ncodes);
+        for (uint64_t x = 0; x < h->ncodes; ++x) {
+            const uint32_t a = rank_full[x], b = (uint32_t)x;
+            tc[x] = (uint16_t)((a >> 2) * 128u + (a & 3u));
+            tr[x] = (uint16_t)((b >> 2) * 128u + (b & 3u));
+        }
+        CUB(cudaMalloc(&h->d_short_tab_canon, h->ncodes * 2));
+        CUB(cudaMalloc(&h->d_short_tab_raw, h->ncodes * 2));
+        CUB(cudaMemcpy(h->d_short_tab_canon, tc.data(), h->ncodes * 2, cudaMemcpyHostToDevice));
+        CUB(cudaMemcpy(h->d_short_tab_raw, tr.data(), h->ncodes * 2, cudaMemcpyHostToDevice));
+    }
+    CUB(cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)));
+    for (auto &s : h->sets) {
+        CUB(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        for (auto &e : s.ev) CUB(cudaEventCreate(&e));
+    }
+#undef CUB
+    *out = h;
+    return KTB_OK;
+}
+
+void ktb_oligo_destroy(ktb_oligo *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto &s : h->sets) {
+        if (s.stream) {
+            cudaStreamSynchronize(s.stream);
+            cudaStreamDestroy(s.stream);
+        }
+        for (auto &e : s.ev)
+            if (e) cudaEventDestroy(e);
+        s.bases.release();
+        s.offsets.release();
+        s.out.release();
+        s.totals.release();
+    }
+    h->ws_totals.release();
+    h->ws_counts.release();
+    if (h->d_rank_full) cudaFree(h->d_rank_full);
+    if (h->d_canon_of_rank) cudaFree(h->d_canon_of_rank);
+    if (h->d_short_tab_canon) cudaFree(h->d_short_tab_canon);
+    if (h->d_short_tab_raw) cudaFree(h->d_short_tab_raw);
+    if (h->d_counters) cudaFree(h->d_counters);
+    delete h;
+}
+
+int ktb_oligo_k(const ktb_oligo *h) { return h ? h->k : 0; }
+
+uint64_t ktb_oligo_dim(const ktb_oligo *h, int canonical) {
+    if (!h) return 0;
+    return canonical ? h->dim_canon : h->ncodes;
+}
+
+int ktb_oligo_header(const ktb_oligo *h, int canonical, char *buf, size_t cap) {
+    if (!h || !buf) return fail(KTB_ERR_ARG, "null argument");
+    const uint64_t dim = ktb_oligo_dim(h, canonical);
+    if (cap < dim * (uint64_t)h->k) return fail(KTB_ERR_ARG, "header buffer too small (%zu < %llu)", cap,
+                                               (unsigned long long)(dim * h->k));
+    static const char L[4] = {'A', 'C', 'G', 'T'};
+    for (uint64_t j = 0; j < dim; ++j) {  // numeric_to_kmer, kmer/src/lib.rs:19-34
+        uint64_t code = canonical ? h->canon_of_rank[j] : j;
+        for (int i = h->k - 1; i >= 0; --i) {
+            buf[j * h->k + i] = L[code & 3];
+            code >>= 2;
+        }
+    }
+    return KTB_OK;
+}
+
+int ktb_oligo_pos_maps(const ktb_oligo *h, uint64_t *pos_map, uint64_t *pos_to_kmer, uint64_t *count) {
+    if (!h) return fail(KTB_ERR_ARG, "null handle");
+    if (pos_map)
+        for (uint64_t x = 0; x < h->ncodes; ++x) pos_map[x] = h->rank_of_canon[x];
+    if (pos_to_kmer)
+        for (uint64_t j = 0; j < h->dim_canon; ++j) pos_to_kmer[j] = h->canon_of_rank[j];
+    if (count) *count = h->dim_canon;
+    return KTB_OK;
+}
+
+int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
+    if (!h || !key) return fail(KTB_ERR_ARG, "null argument");
+    if (!strcmp(key, "chunk_bytes")) {
+        if (value < (1 << 16)) return fail(KTB_ERR_ARG, "chunk_bytes too small");
+        h->chunk_bytes = value;
+    } else if (!strcmp(key, "force_path")) {
+        h->force_path = (int)value;
+    } else if (!strcmp(key, "short_variant")) {
+        h->short_variant = (int)value;
+    } else if (!strcmp(key, "short_warps")) {
+        h->short_warps = (int)value;
+    } else {
+        return fail(KTB_ERR_ARG, "unknown option '%s'", key);
+    }
+    return KTB_OK;
+}
+
+int ktb_oligo_last_stats(const ktb_oligo *h, ktb_stats *out) {
+    if (!h || !out) return fail(KTB_ERR_ARG, "null argument");
+    *out = h->stats;
+    return KTB_OK;
+}
+
+int ktb_oligo_vectorise_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n,
+                               uint64_t total_bases, int canonical, int norm_mode, int out_dtype,
+                               void *d_out, uint64_t *d_totals, void *stream) {
+    if (int rc = check_args(h, canonical, norm_mode, out_dtype)) return rc;
+    if (n && (!d_offsets || !d_out)) return fail(KTB_ERR_ARG, "null device pointer");
+    if (total_bases && !d_bases) return fail(KTB_ERR_ARG, "null bases pointer");
+    if (((uintptr_t)d_bases & 15) || ((uintptr_t)d_out & 15))
+        return fail(KTB_ERR_ARG, "d_bases and d_out must be 16-byte aligned");
+    if (int rc = set_device(h)) return rc;
+    h->stats = ktb_stats{};
+    return dispatch_device(h, d_bases, d_offsets, n, total_bases, canonical, norm_mode, out_dtype, d_out,
+                           d_totals, (cudaStream_t)stream);
+}
+
+int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offsets, uint64_t n, int canonical,
+                        int norm_mode, int out_dtype, void *out, uint64_t *totals) {
+    if (int rc = check_args(h, canonical, norm_mode, out_dtype)) return rc;
+    if (n && (!offsets || !out)) return fail(KTB_ERR_ARG, "null pointer");
+    if (int rc = set_device(h)) return rc;
+    const double t0 = now_ms();
+    h->stats = ktb_stats{};
+    if (n == 0) return KTB_OK;
+    for (uint64_t i = 0; i < n; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(KTB_ERR_ARG, "offsets must be non-decreasing (at %llu)",
+                                                     (unsigned long long)i);
+    if (offsets[n] > offsets[0] && !bases) return fail(KTB_ERR_ARG, "null bases pointer");
+
+    const uint64_t dim = ktb_oligo_dim(h, canonical);
+    const size_t esize = out_dtype == KTB_OUT_F64 ? 8 : 4;
+    const uint64_t row_bytes = dim * esize;
+    uint64_t rows_per_chunk = std::max<uint64_t>(1, (uint64_t)h->chunk_bytes / row_bytes);
+    const uint64_t max_chunk_bases = 1ull << 30;
+
+    struct Pending { uint64_t i0, i1; };
+    Pending pend[NBUF];
+    bool has[NBUF] = {false, false, false};
+    auto drain = [&](int b) -> int {
+        ChunkSet &s = h->sets[b];
+        if (!has[b]) return KTB_OK;
+        CU(cudaStreamSynchronize(s.stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1])); h->stats.h2d_ms += ms;
+        CU(cudaEventElapsedTime(&ms, s.ev[1], s.ev[2])); h->stats.kernel_ms += ms;
+        CU(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3])); h->stats.d2h_ms += ms;
+        has[b] = false;
+        return KTB_OK;
+    };
+
+    int b = 0;
+    const uint64_t launches_before = 0;
+    (void)launches_before;
+    uint64_t total_launches = 0;
+    for (uint64_t i0 = 0; i0 < n;) {
+        uint64_t i1 = std::min(n, i0 + rows_per_chunk);
+        // cap the bases per chunk (always keep at least one sequence)
+        if (offsets[i1] - offsets[i0] > max_chunk_bases && i1 > i0 + 1) {
+            const uint64_t *lo = offsets + i0 + 1, *hi = offsets + i1;
+            const uint64_t *it = std::upper_bound(lo, hi, offsets[i0] + max_chunk_bases);
+            i1 = std::max<uint64_t>(i0 + 1, (uint64_t)(it - offsets) - 1);
+        }
+        const uint64_t cn = i1 - i0;
+        const uint64_t b0 = offsets[i0] & ~15ull;  // keep the 16-byte phase of the caller's buffer
+        const uint64_t nb = offsets[i1] - b0;
+        ChunkSet &s = h->sets[b];
+        if (int rc = drain(b)) return rc;
+        if (int rc = s.bases.ensure(nb + 64)) return rc;
+        if (int rc = s.offsets.ensure((cn + 1) * 8)) return rc;
+        if (int rc = s.out.ensure(cn * row_bytes)) return rc;
+        if (totals)
+            if (int rc = s.totals.ensure(cn * 8)) return rc;
+        CU(cudaEventRecord(s.ev[0], s.stream));
+        if (nb) CU(cudaMemcpyAsync(s.bases.p, bases + b0, nb, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.offsets.p, offsets + i0, (cn + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaEventRecord(s.ev[1], s.stream));
+        if (b0) {
+            rebase_offsets_kernel<<<(unsigned)std::min<uint64_t>((cn + 256) / 256, 1024), 256, 0, s.stream>>>(
+                (uint64_t *)s.offsets.p, cn + 1, b0);
+            CU(cudaGetLastError());
+            total_launches++;
+        }
+        const ktb_stats keep = h->stats;
+        if (int rc = dispatch_device(h, (const uint8_t *)s.bases.p, (const uint64_t *)s.offsets.p, cn, nb,
+                                     canonical, norm_mode, out_dtype, s.out.p,
+                                     totals ? (uint64_t *)s.totals.p : nullptr, s.stream))
+            return rc;
+        total_launches += h->stats.launches - keep.launches;
+        CU(cudaEventRecord(s.ev[2], s.stream));
+        CU(cudaMemcpyAsync((uint8_t *)out + i0 * row_bytes, s.out.p, cn * row_bytes, cudaMemcpyDeviceToHost,
+                           s.stream));
+        if (totals) CU(cudaMemcpyAsync(totals + i0, s.totals.p, cn * 8, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaEventRecord(s.ev[3], s.stream));
+        h->stats.h2d_bytes += nb + (cn + 1) * 8;
+        h->stats.d2h_bytes += cn * row_bytes + (totals ? cn * 8 : 0);
+        has[b] = true;
+        pend[b] = {i0, i1};
+        b = (b + 1) % NBUF;
+        i0 = i1;
+    }
+    (void)pend;
+    for (int q = 0; q < NBUF; ++q)
+        if (int rc = drain(q)) return rc;
+    h->stats.launches = total_launches;
+    h->stats.wall_ms = now_ms() - t0;
+    return KTB_OK;
+}
+
+void *ktb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        fail(KTB_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+
+void ktb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int ktb_debug_nt4_table(ktb_oligo *h, uint8_t *out256) {
+    if (!h || !out256) return fail(KTB_ERR_ARG, "null argument");
+    if (int rc = set_device(h)) return rc;
+    uint8_t *d = nullptr;
+    CU(cudaMalloc(&d, 256));
+    ktb::nt4_table_kernel<<<1, 256>>>(d);
+    cudaError_t e = cudaMemcpy(out256, d, 256, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(KTB_ERR_CUDA, "nt4 table copy failed: %s", cudaGetErrorString(e));
+    return KTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,559 @@
+// kernels.cuh — sm_100a device code of the oligonucleotide-frequency-vector path.
+//
+// What is computed (closed form of kmer/src/kmer.rs:80-106 + composition/src/oligo.rs:231-259,
+// see DESIGN.md §2):
+//   c[p]      = nt4(seq[p])                       0..3 valid, 4 ambiguous       (kmer.rs:6-15)
+//   valid(p)  = the k bases ending at p are all < 4
+//   f(p)      = sum_j c[p-k+1+j] * 4^(k-1-j)       forward code, oldest base most significant
+//   r(p)      = sum_j (3-c[p-k+1+j]) * 4^j         reverse complement in the same encoding
+//   row[rank(min(f,r))] += 1  (canonical)   |   row[f] += 1  (raw)          for every valid p
+//   row[j]   /= max(1, total)                      when normalising
+//
+// Three kernels cover the (length, k) plane:
+//   short_kernel  : one THREAD per read, byte-wide private histograms in shared memory (no atomics),
+//                   warp-transposed coalesced write-out.  Reads with <=255 windows, 4^k <= 1024.
+//   seq_kernel    : one CTA per sequence, 16 bases per lane per step from one 128-bit load, k-mers
+//                   cut out of a 2-bit packed 64-bit window, shared-memory atomics, fused
+//                   normalisation on write-out.  Any length, histogram fits shared memory.
+//   flat_kernel   : flat decomposition of the base stream, global-memory atomics into zeroed rows
+//                   (+ finalize_kernel).  Any k <= 12.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ktb {
+
+constexpr int OUT_U32 = 0, OUT_F32 = 1, OUT_F64 = 2;
+constexpr int NORM_COUNTS = 0, NORM_CLI = 1, NORM_PY = 2;
+
+// ------------------------------------------------------------------------------------------------
+// byte -> 2-bit code, 4 = ambiguous.  Same mapping as SEQ_NT4_TABLE (kmer/src/kmer.rs:6-15):
+// bytes 0..3 -> themselves, A/a 0, C/c 1, G/g 2, T/t/U/u 3, everything else 4.  Arithmetic instead
+// of a table: ((b>>1)^(b>>2))&3 sends A,C,G,T/U (either case) to 0,1,2,3.
+__device__ __forceinline__ uint32_t nt4_code(uint32_t b) {
+    const uint32_t u = b & 0xDFu;
+    const uint32_t code = ((b >> 1) ^ (b >> 2)) & 3u;
+    const bool letter = (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T') | (u == 'U');
+    return b < 4u ? b : (letter ? code : 4u);
+}
+
+__global__ void nt4_table_kernel(uint8_t *out) { out[threadIdx.x] = (uint8_t)nt4_code(threadIdx.x); }
+
+// Correctly rounded c / d in f32 for integers 0 <= c <= d < 2^24: q0 = c * RN(1/d), one exact
+// residual and one correction FMA.  Because c/d has a denominator below 2^24 it can never sit within
+// 2^-49 (relative) of an f32 rounding boundary without being on it, so this equals
+// (float)((double)c / (double)d), i.e. the reference's f64 quotient rounded once.  Checked
+// exhaustively for d <= 4096 on the CPU in tests/test_host_logic.py (same FMA sequence in C).
+__device__ __forceinline__ float quot_f32(float c, float d, float rinv) {
+    const float q0 = c * rinv;
+    const float rem = fmaf(-q0, d, c);
+    return fmaf(rem, rinv, q0);
+}
+
+// divisor of the normalisation step as an integer (oligo.rs:255-257; pybindings/src/oligo.rs:58-66)
+__device__ __forceinline__ uint64_t norm_divisor(uint64_t total, int norm_mode, int canonical) {
+    uint64_t t = (norm_mode == NORM_PY && !canonical) ? 2 * total : total;
+    return t > 1 ? t : 1;
+}
+
+template <int OUT> struct OutT;
+template <> struct OutT<OUT_U32> { using type = uint32_t; };
+template <> struct OutT<OUT_F32> { using type = float; };
+template <> struct OutT<OUT_F64> { using type = double; };
+
+// Converts one count to the output element.  dF/rinv are used for f32 when the divisor is exactly
+// representable (< 2^24); otherwise, and for f64, the division is done in double like the reference.
+template <int OUT>
+__device__ __forceinline__ typename OutT<OUT>::type make_out(uint32_t cnt, bool norm, bool small_div,
+                                                             float dF, float rinv, double dD) {
+    if constexpr (OUT == OUT_U32) {
+        return cnt;
+    } else if constexpr (OUT == OUT_F32) {
+        if (!norm) return (float)cnt;
+        if (small_div) return quot_f32((float)cnt, dF, rinv);
+        return (float)((double)cnt / dD);
+    } else {
+        if (!norm) return (double)cnt;
+        return (double)cnt / dD;
+    }
+}
+
+// ================================================================================================
+// short_kernel — thread per read
+// ================================================================================================
+struct ShortParams {
+    const uint8_t *bases;
+    const uint64_t *offsets;
+    uint64_t n;
+    uint64_t ngroups;        // ceil(n / 32)
+    void *out;
+    uint64_t *totals;        // optional
+    const uint16_t *tab;     // [4^k] code -> byte offset of its bin inside a lane's histogram
+    unsigned long long *counter;  // dynamic group counter (zeroed before launch)
+    uint32_t k;
+    uint32_t ncodes;         // 4^k  (<= 1024)
+    uint32_t dim;            // row width, multiple of 4
+    uint32_t words;          // dim / 4 : 32-bit histogram words per read
+    uint32_t stage_bytes;    // per-warp staging buffer, multiple of 16, >= 32*33*4
+    uint32_t max_len;        // longest read this kernel takes: 254 + k
+    int norm_mode;
+    int canonical;
+    int warps;               // warps per CTA
+};
+
+constexpr int SHORT_MAX_CODES = 1024;
+
+// Histogram layout (per warp): word w of lane t lives at hist[w * 32 + t], so every lane only ever
+// touches bank t: the scattered increments of the accumulate phase are bank-conflict free without
+// atomics.  Counts are bytes (<= 255 windows per read), four bins per word, and one word converts
+// to exactly one 128-bit store of four floats on the way out.
+template <int OUT, bool ATOM>
+__global__ void __launch_bounds__(512, 1) short_kernel(const ShortParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint16_t s_tab[SHORT_MAX_CODES];
+    __shared__ uint8_t s_lut[256];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < p.ncodes; i += blockDim.x) s_tab[i] = p.tab[i];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = (uint8_t)nt4_code(i);
+
+    const uint32_t hist_bytes = p.words * 128u;
+    uint8_t *my = smem + (size_t)warp * (hist_bytes + p.stage_bytes);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(my);
+    uint8_t *stage = my + hist_bytes;
+    for (uint32_t i = lane; i < p.words * 32u; i += 32) hist[i] = 0;
+    __syncthreads();
+
+    const uint32_t kmask = (p.k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * p.k)) - 1u);
+    using T = typename OutT<OUT>::type;
+    T *out = reinterpret_cast<T *>(p.out);
+    const bool norm = p.norm_mode != NORM_COUNTS;
+
+    for (;;) {
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(p.counter, 1ULL);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= p.ngroups) break;
+        const uint64_t i0 = g * 32ULL;
+        const uint64_t i = i0 + lane;
+        const uint64_t o0 = (i <= p.n) ? p.offsets[i] : p.offsets[p.n];
+        const uint64_t o1 = (i + 1 <= p.n) ? p.offsets[i + 1] : o0;
+        const uint32_t len = (uint32_t)min((unsigned long long)(o1 - o0), 0xFFFFFFFFULL);
+        const uint64_t span0 = __shfl_sync(0xffffffffu, o0, 0) & ~15ULL;  // 16B-aligned span start
+        const uint64_t span1 = __shfl_sync(0xffffffffu, o1, 31);
+        // group eligibility: every read short enough for byte counters, span fits the stage buffer
+        const bool ok = __all_sync(0xffffffffu, len <= p.max_len) &&
+                        (span1 - span0 + 16 <= p.stage_bytes);
+        if (!ok) continue;  // seq_kernel takes this group
+
+        // ---- stage the group's bases (coalesced 128-bit loads; tail bytewise)
+        const uint64_t nbytes = span1 - span0;
+        const uint64_t nvec = nbytes >> 4;
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.bases + span0);
+        uint4 *dst = reinterpret_cast<uint4 *>(stage);
+        for (uint64_t v = lane; v < nvec; v += 32) dst[v] = __ldg(src + v);
+        for (uint64_t b = (nvec << 4) + lane; b < nbytes; b += 32) stage[b] = p.bases[span0 + b];
+        __syncwarp();
+
+        // ---- accumulate: each lane walks its own read
+        const uint32_t sb = (uint32_t)(o0 - span0);
+        const uint32_t a = sb & 3u;
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(stage) + (sb >> 2);
+        const uint32_t nwords = (len == 0) ? 0u : ((a + len + 3u) >> 2);
+        uint32_t maxwords = nwords;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) maxwords = max(maxwords, __shfl_xor_sync(0xffffffffu, maxwords, s));
+        uint8_t *hb = my + lane * 4;
+        uint32_t f = 0, run = 0, tot = 0;
+        for (uint32_t wi = 0; wi < maxwords; ++wi) {
+            const uint32_t w = (wi < nwords) ? wp[wi] : 0xFFFFFFFFu;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t pos = wi * 4u + j - a;  // wraps for the bytes before the read
+                const uint32_t b = (w >> (8 * j)) & 0xFFu;
+                uint32_t c = s_lut[b];
+                c = (pos < len) ? c : 4u;
+                f = ((f << 2) | (c & 3u)) & kmask;
+                run = (c < 4u) ? run + 1u : 0u;
+                if (run >= p.k) {
+                    const uint32_t off = s_tab[f];
+                    if constexpr (ATOM) {
+                        atomicAdd(reinterpret_cast<uint32_t *>(hb + (off & 0xFFFCu)), 1u << ((off & 3u) * 8u));
+                    } else {
+                        hb[off] = (uint8_t)(hb[off] + 1u);
+                    }
+                    ++tot;
+                }
+            }
+        }
+        if (p.totals && i < p.n) p.totals[i] = tot;
+        __syncwarp();
+
+        // ---- write-out: 32x32 word transposes through the (now free) stage buffer, zeroing as we go
+        uint32_t *tr = reinterpret_cast<uint32_t *>(stage);  // [32][33]
+        const uint64_t dv = norm_divisor(tot, p.norm_mode, p.canonical);
+        const float dF = (float)dv;
+        const float rinv = __frcp_rn(dF);
+        for (uint32_t wb = 0; wb < p.words; wb += 32) {
+            const uint32_t nw = min(32u, p.words - wb);
+            for (uint32_t j = 0; j < nw; ++j) {
+                const uint32_t v = hist[(wb + j) * 32u + lane];
+                hist[(wb + j) * 32u + lane] = 0;
+                tr[lane * 33 + j] = v;
+            }
+            __syncwarp();
+            const uint32_t nreads = (uint32_t)min((unsigned long long)32, (unsigned long long)(p.n - i0));
+            for (uint32_t r = 0; r < nreads; ++r) {
+                const float dFr = __shfl_sync(0xffffffffu, dF, r);
+                const float rinvr = __shfl_sync(0xffffffffu, rinv, r);
+                if (lane < nw) {
+                    const uint32_t v = tr[r * 33 + lane];
+                    T *dstp = out + (i0 + r) * (uint64_t)p.dim + (uint64_t)(wb + lane) * 4u;
+                    const double dD = (double)dFr;
+                    T e0 = make_out<OUT>(v & 0xFFu, norm, true, dFr, rinvr, dD);
+                    T e1 = make_out<OUT>((v >> 8) & 0xFFu, norm, true, dFr, rinvr, dD);
+                    T e2 = make_out<OUT>((v >> 16) & 0xFFu, norm, true, dFr, rinvr, dD);
+                    T e3 = make_out<OUT>(v >> 24, norm, true, dFr, rinvr, dD);
+                    if constexpr (OUT == OUT_F64) {
+                        reinterpret_cast<double2 *>(dstp)[0] = make_double2(e0, e1);
+                        reinterpret_cast<double2 *>(dstp)[1] = make_double2(e2, e3);
+                    } else if constexpr (OUT == OUT_F32) {
+                        *reinterpret_cast<float4 *>(dstp) = make_float4(e0, e1, e2, e3);
+                    } else {
+                        *reinterpret_cast<uint4 *>(dstp) = make_uint4(e0, e1, e2, e3);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ================================================================================================
+// seq_kernel — CTA per sequence, shared-memory atomics
+// ================================================================================================
+struct SeqParams {
+    const uint8_t *bases;        // 16-byte aligned
+    const uint64_t *offsets;
+    uint64_t n;
+    uint64_t total_bases;
+    void *out;
+    uint64_t *totals;            // optional
+    const uint32_t *rank_full;   // [4^k] code -> rank of its canonical form (rank-space mode)
+    const uint32_t *canon_of_rank;  // [dim] rank -> canonical code       (code-space mode)
+    unsigned long long *counter; // dynamic group counter (zeroed before launch)
+    uint32_t k;
+    uint32_t dim;
+    uint32_t hist_entries;       // shared-memory histogram entries (4^k in code space, dim in rank space)
+    int norm_mode;
+    int canonical;
+    int skip_short;              // 1: groups that short_kernel accepts are skipped here
+    uint32_t short_max_len;
+    uint32_t short_stage_bytes;
+};
+
+// 16 bases -> packed 2-bit codes (base j at bits 2*(15-j)+1..2*(15-j), oldest base most significant)
+// and a 16-bit validity mask (base j at bit 15-j).
+__device__ __forceinline__ void decode16(const uint4 v, uint32_t &cf, uint32_t &vm) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m[4];
+    bool all_ok = true;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t c4 = ((w[q] >> 1) ^ (w[q] >> 2)) & 0x03030303u;
+        m[q] = c4 * 0x40100401u;  // top byte = b0<<6 | b1<<4 | b2<<2 | b3
+        // validity: rebuild the upper-case letter each code stands for and compare with the input
+        const uint32_t y = (c4 | (c4 >> 4)) & 0x00FF00FFu;
+        const uint32_t sel = (y | (y >> 8)) & 0xFFFFu;
+        const uint32_t recon = __byte_perm(0x54474341u, 0u, sel);  // "ACGT"[code]
+        all_ok &= (recon == (w[q] & 0xDFDFDFDFu));
+    }
+    const uint32_t u01 = __byte_perm(m[1], m[0], 0x0073);
+    const uint32_t u23 = __byte_perm(m[3], m[2], 0x0073);
+    cf = __byte_perm(u23, u01, 0x5410);
+    vm = 0xFFFFu;
+    if (!all_ok) {  // rare: N / IUPAC / U / raw 0..3 codes — exact per-byte path
+        cf = 0;
+        vm = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t c = nt4_code((w[q] >> (8 * j)) & 0xFFu);
+                cf = (cf << 2) | (c & 3u);
+                vm = (vm << 1) | (c < 4u ? 1u : 0u);
+            }
+        }
+    }
+}
+
+// reverse-complement packing of 16 bases: base j at bits 2j+1..2j, complemented
+__device__ __forceinline__ uint32_t revcomp_pack(uint32_t cf) {
+    uint32_t x = __brev(~cf);
+    return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+
+// HIST_MODE: 0 = raw (index f), 1 = canonical code space (index min(f,r), gather on write-out),
+//            2 = canonical rank space (index rank_full[f], linear write-out)
+template <int OUT, int HIST_MODE>
+__global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
+    extern __shared__ __align__(16) uint32_t hist[];
+    __shared__ unsigned long long s_group;
+    __shared__ int s_skip;
+    __shared__ uint32_t s_total[2];  // double-buffered so the reset never races a late reader
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    for (uint32_t i = tid; i < p.hist_entries; i += blockDim.x) hist[i] = 0;
+    if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
+    __syncthreads();
+    uint32_t it = 0;
+
+    const uint32_t k = p.k;
+    const uint32_t kmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    using T = typename OutT<OUT>::type;
+    T *out = reinterpret_cast<T *>(p.out);
+    const bool norm = p.norm_mode != NORM_COUNTS;
+    const uint64_t ngroups = (p.n + 31) / 32;
+    const bool vec_ok = (p.dim & 3u) == 0;
+
+    for (;;) {
+        if (tid == 0) s_group = atomicAdd(p.counter, 1ULL);
+        __syncthreads();
+        const unsigned long long g = s_group;
+        if (g >= ngroups) break;
+        const uint64_t i0 = g * 32ULL;
+        if (warp == 0) {
+            int skip = 0;
+            if (p.skip_short) {
+                const uint64_t i = i0 + lane;
+                const uint64_t o0 = (i <= p.n) ? p.offsets[i] : p.offsets[p.n];
+                const uint64_t o1 = (i + 1 <= p.n) ? p.offsets[i + 1] : o0;
+                const uint64_t span0 = __shfl_sync(0xffffffffu, o0, 0) & ~15ULL;
+                const uint64_t span1 = __shfl_sync(0xffffffffu, o1, 31);
+                skip = __all_sync(0xffffffffu, (o1 - o0) <= p.short_max_len) &&
+                       (span1 - span0 + 16 <= p.short_stage_bytes);
+            }
+            if (lane == 0) s_skip = skip;
+        }
+        __syncthreads();
+        if (s_skip) continue;
+        const uint32_t nseq = (uint32_t)min((unsigned long long)32, (unsigned long long)(p.n - i0));
+
+        for (uint32_t si = 0; si < nseq; ++si) {
+            const uint64_t seq = i0 + si;
+            const uint64_t s0 = p.offsets[seq];
+            const uint64_t s1 = p.offsets[seq + 1];
+            uint32_t mine = 0;  // valid windows counted by this thread
+            if (s1 - s0 >= k) {
+                // chunk c covers bases [16c, 16c+16); lane 0 of every warp re-reads the chunk before
+                // its warp's first emitting chunk as look-back, so a warp advances 31 chunks per step
+                const int64_t c_first = (int64_t)(s0 >> 4);
+                const int64_t c_last = (int64_t)((s1 - 1) >> 4);
+                for (int64_t cb = c_first + (int64_t)warp * 31; cb <= c_last; cb += (int64_t)nwarps * 31) {
+                    const int64_t c = cb + lane - 1;
+                    uint32_t cf = 0, vm = 0;
+                    if (c >= c_first && c <= c_last) {
+                        const uint64_t a = (uint64_t)c << 4;
+                        uint4 v;
+                        if (a + 16 <= p.total_bases) {
+                            v = __ldg(reinterpret_cast<const uint4 *>(p.bases + a));
+                        } else {
+                            uint32_t t[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+                            for (uint64_t b = a; b < p.total_bases; ++b) {
+                                const uint32_t sh = (uint32_t)(b - a);
+                                t[sh >> 2] = (t[sh >> 2] & ~(0xFFu << ((sh & 3) * 8))) |
+                                             ((uint32_t)p.bases[b] << ((sh & 3) * 8));
+                            }
+                            v = make_uint4(t[0], t[1], t[2], t[3]);
+                        }
+                        decode16(v, cf, vm);
+                        // keep only bases inside [s0, s1)
+                        const uint32_t lo = (s0 > a) ? (uint32_t)(s0 - a) : 0u;
+                        const uint32_t hi = (s1 - a < 16) ? (uint32_t)(s1 - a) : 16u;
+                        const uint32_t rm = ((1u << (16 - lo)) - 1u) & ~((1u << (16 - hi)) - 1u);
+                        vm &= rm;
+                    }
+                    const uint32_t cf_prev = __shfl_up_sync(0xffffffffu, cf, 1);
+                    const uint32_t vm_prev = __shfl_up_sync(0xffffffffu, vm, 1);
+                    if (lane == 0 || vm == 0) continue;  // lane 0 only supplies look-back
+                    // windows: bit b of vw set <=> V32 bits b..b+k-1 all set (older bases = higher bits)
+                    const uint32_t V32 = (vm_prev << 16) | vm;
+                    uint32_t vw = V32;
+                    {
+                        uint32_t have = 1;
+                        while (have < k) {
+                            const uint32_t step = min(have, k - have);
+                            vw &= vw >> step;
+                            have += step;
+                        }
+                    }
+                    vw &= 0xFFFFu;
+                    if (vw == 0) continue;
+                    mine += __popc(vw);
+                    const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
+                    uint64_t R64 = 0;
+                    if constexpr (HIST_MODE == 1) {
+                        R64 = ((uint64_t)revcomp_pack(cf) << 32) | revcomp_pack(cf_prev);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (vw & (1u << (15 - j))) {
+                            const uint32_t f = (uint32_t)(F64 >> (2 * (15 - j))) & kmask;
+                            uint32_t idx;
+                            if constexpr (HIST_MODE == 0) {
+                                idx = f;
+                            } else if constexpr (HIST_MODE == 1) {
+                                const uint32_t r = (uint32_t)(R64 >> (2 * (17 + j - (int)k))) & kmask;
+                                idx = min(f, r);
+                            } else {
+                                idx = __ldg(p.rank_full + f);
+                            }
+                            atomicAdd(&hist[idx], 1u);
+                        }
+                    }
+                }
+            }
+            // ---- total = block sum of `mine`
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, s);
+            if (lane == 0 && mine) atomicAdd(&s_total[it & 1], mine);
+            __syncthreads();
+            const uint32_t total = s_total[it & 1];
+            if (tid == 0) s_total[(it + 1) & 1] = 0;  // slot of the next sequence; last read two barriers ago
+            ++it;
+            const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
+            const bool small_div = dv < (1ULL << 24);
+            const float dF = (float)dv;
+            const float rinv = __frcp_rn(dF);
+            const double dD = (double)dv;
+            if (tid == 0 && p.totals) p.totals[seq] = total;
+            // ---- write-out (normalisation fused), histogram re-zeroed on the way
+            T *row = out + seq * (uint64_t)p.dim;
+            if (vec_ok) {
+                for (uint32_t j = tid * 4u; j < p.dim; j += blockDim.x * 4u) {
+                    uint32_t cnt[4];
+                    if constexpr (HIST_MODE == 1) {
+                        const uint4 cc = __ldg(reinterpret_cast<const uint4 *>(p.canon_of_rank + j));
+                        cnt[0] = hist[cc.x]; cnt[1] = hist[cc.y]; cnt[2] = hist[cc.z]; cnt[3] = hist[cc.w];
+                        hist[cc.x] = 0; hist[cc.y] = 0; hist[cc.z] = 0; hist[cc.w] = 0;
+                    } else {
+                        const uint4 hv = *reinterpret_cast<const uint4 *>(hist + j);
+                        cnt[0] = hv.x; cnt[1] = hv.y; cnt[2] = hv.z; cnt[3] = hv.w;
+                        *reinterpret_cast<uint4 *>(hist + j) = make_uint4(0, 0, 0, 0);
+                    }
+                    T e0 = make_out<OUT>(cnt[0], norm, small_div, dF, rinv, dD);
+                    T e1 = make_out<OUT>(cnt[1], norm, small_div, dF, rinv, dD);
+                    T e2 = make_out<OUT>(cnt[2], norm, small_div, dF, rinv, dD);
+                    T e3 = make_out<OUT>(cnt[3], norm, small_div, dF, rinv, dD);
+                    if constexpr (OUT == OUT_F64) {
+                        reinterpret_cast<double2 *>(row + j)[0] = make_double2(e0, e1);
+                        reinterpret_cast<double2 *>(row + j)[1] = make_double2(e2, e3);
+                    } else if constexpr (OUT == OUT_F32) {
+                        *reinterpret_cast<float4 *>(row + j) = make_float4(e0, e1, e2, e3);
+                    } else {
+                        *reinterpret_cast<uint4 *>(row + j) = make_uint4(e0, e1, e2, e3);
+                    }
+                }
+            } else {
+                for (uint32_t j = tid; j < p.dim; j += blockDim.x) {
+                    uint32_t cnt;
+                    if constexpr (HIST_MODE == 1) {
+                        const uint32_t cc = __ldg(p.canon_of_rank + j);
+                        cnt = hist[cc];
+                        hist[cc] = 0;
+                    } else {
+                        cnt = hist[j];
+                        hist[j] = 0;
+                    }
+                    row[j] = make_out<OUT>(cnt, norm, small_div, dF, rinv, dD);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ================================================================================================
+// flat_kernel — flat decomposition of the base stream + global atomics (any k <= 12)
+// ================================================================================================
+struct FlatParams {
+    const uint8_t *bases;
+    const uint64_t *offsets;
+    uint64_t n;
+    uint64_t total_bases;
+    uint32_t *counts;            // n x dim, zeroed
+    unsigned long long *totals;  // n, zeroed
+    const uint32_t *rank_full;   // [4^k] or nullptr in raw mode
+    uint64_t dim;
+    uint32_t k;
+};
+
+constexpr int FLAT_CHUNK = 32;
+
+__global__ void __launch_bounds__(256) flat_kernel(const FlatParams p) {
+    const uint32_t k = p.k;
+    const uint32_t kmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    const uint64_t nchunks = (p.total_bases + FLAT_CHUNK - 1) / FLAT_CHUNK;
+    for (uint64_t ch = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks;
+         ch += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p0 = ch * FLAT_CHUNK;
+        const uint64_t p1 = min(p0 + (uint64_t)FLAT_CHUNK, p.total_bases);
+        // sequence containing p0: largest s with offsets[s] <= p0 < offsets[s+1]
+        uint64_t lo = 0, hi = p.n;  // invariant: offsets[lo] <= p0, offsets[hi] > p0 (offsets[n] = total > p0)
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (p.offsets[mid] <= p0) lo = mid; else hi = mid;
+        }
+        uint64_t s = lo;
+        uint64_t s_end = p.offsets[s + 1];
+        const uint64_t s_begin = p.offsets[s];
+        uint64_t q = (p0 >= (uint64_t)(k - 1)) ? p0 - (k - 1) : 0;
+        if (q < s_begin) q = s_begin;
+        uint32_t f = 0, run = 0;
+        unsigned long long tot = 0;
+        for (uint64_t pos = q; pos < p1; ++pos) {
+            while (pos >= s_end) {  // crossed into the next (possibly empty) sequence
+                if (tot) { atomicAdd(p.totals + s, tot); tot = 0; }
+                ++s;
+                s_end = p.offsets[s + 1];
+                run = 0;
+            }
+            const uint32_t c = nt4_code(p.bases[pos]);
+            f = ((f << 2) | (c & 3u)) & kmask;
+            run = (c < 4u) ? run + 1u : 0u;
+            if (run >= k && pos >= p0) {
+                const uint32_t idx = p.rank_full ? __ldg(p.rank_full + f) : f;
+                atomicAdd(p.counts + s * p.dim + idx, 1u);
+                ++tot;
+            }
+        }
+        if (tot) atomicAdd(p.totals + s, tot);
+    }
+}
+
+// counts (u32, n x dim) -> out (n x dim of OUT); in place when OUT is 4 bytes wide and out == counts
+template <int OUT>
+__global__ void __launch_bounds__(256) finalize_kernel(const uint32_t *counts, const unsigned long long *totals,
+                                                       void *outv, uint64_t *totals_out, uint64_t n,
+                                                       uint64_t dim, int norm_mode, int canonical) {
+    using T = typename OutT<OUT>::type;
+    T *out = reinterpret_cast<T *>(outv);
+    const bool norm = norm_mode != NORM_COUNTS;
+    const uint64_t nel = n * dim;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nel;
+         e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = e / dim;
+        const unsigned long long total = totals[s];
+        const uint64_t dv = norm_divisor(total, norm_mode, canonical);
+        const bool small_div = dv < (1ULL << 24);
+        const float dF = (float)dv;
+        out[e] = make_out<OUT>(counts[e], norm, small_div, dF, __frcp_rn(dF), (double)dv);
+        if (totals_out && e == s * dim) totals_out[s] = total;
+    }
+}
+
+}  // namespace ktb

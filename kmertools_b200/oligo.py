@@ -1,0 +1,156 @@
+"""Host-side mirror of the reference's OligoComputer (pybindings/src/oligo.rs:7-99,
+pybindings/pykmertools.pyi:173-235) on top of the C ABI.
+
+Same constructor, method names, argument meaning, defaults and quirks:
+  * OligoComputer(ksize)
+  * vectorise_one(seq, norm=True, mins=True)   -> list[float]
+  * vectorise_batch(seqs, norm=True, mins=True) -> list[list[float]]
+  * get_header(mins=True)                       -> list[str]
+  * raw mode (mins=False) normalises by 2 * #kmers, as pybindings/src/oligo.rs:58-62 does
+  * never raises on sequence content (ambiguous bytes reset the k-mer window)
+Supersets: vectorise_batch_array / vectorise_packed return numpy arrays without the per-float boxing,
+vectorise_device works on CUDA tensors in place.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import NORM_CLI, NORM_COUNTS, NORM_PY, OUT_F32, OUT_F64, OUT_U32
+
+_DTYPES = {OUT_U32: np.uint32, OUT_F32: np.float32, OUT_F64: np.float64}
+_CODES = {np.dtype(np.uint32): OUT_U32, np.dtype(np.float32): OUT_F32, np.dtype(np.float64): OUT_F64}
+
+
+class HostBuffer:
+    """Page-locked host memory from ktb_host_alloc, viewed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self._lib = _lib.load()
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self.ptr = self._lib.ktb_host_alloc(max(nbytes, 1))
+        if not self.ptr:
+            _lib.check(_lib.KTB_ERR_NOMEM)
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape, dtype=np.int64))
+                                   ).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.ktb_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _pack(seqs: Sequence) -> tuple[np.ndarray, np.ndarray]:
+    """list of str/bytes -> (bases u8, offsets u64[n+1]); str is encoded as UTF-8 like Rust's as_bytes()."""
+    bs = [s.encode("utf-8") if isinstance(s, str) else bytes(s) for s in seqs]
+    offsets = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        np.cumsum([len(b) for b in bs], out=offsets[1:])
+    joined = b"".join(bs)
+    bases = np.frombuffer(joined, dtype=np.uint8) if joined else np.zeros(0, dtype=np.uint8)
+    return bases, offsets
+
+
+class OligoComputer:
+    """Computer for generating oligonucleotide frequency vectors (GPU)."""
+
+    def __init__(self, ksize: int, device: int = 0):
+        self._lib = _lib.load()
+        self.ksize = int(ksize)
+        h = C.c_void_p()
+        _lib.check(self._lib.ktb_oligo_create(self.ksize, int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ktb_oligo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ reference interface
+    def vectorise_one(self, seq: str, norm: bool = True, mins: bool = True) -> list[float]:
+        return self.vectorise_batch([seq], norm, mins)[0]
+
+    def vectorise_batch(self, seqs: Iterable[str], norm: bool = True, mins: bool = True) -> list[list[float]]:
+        return self.vectorise_batch_array(list(seqs), norm, mins, dtype=np.float64).tolist()
+
+    def get_header(self, mins: bool = True) -> list[str]:
+        d = self.dim(mins)
+        buf = C.create_string_buffer(d * self.ksize + 1)
+        _lib.check(self._lib.ktb_oligo_header(self._h, int(mins), buf, d * self.ksize))
+        raw = buf.raw[: d * self.ksize].decode()
+        return [raw[i * self.ksize:(i + 1) * self.ksize] for i in range(d)]
+
+    # ------------------------------------------------------------------ supersets
+    def dim(self, mins: bool = True) -> int:
+        return int(self._lib.ktb_oligo_dim(self._h, int(mins)))
+
+    def kmer_pos_maps(self):
+        """(pos_map[4^k], pos_to_kmer[count], count) — KmerGenerator::kmer_pos_maps, kmer.rs:54-73."""
+        n = 4 ** self.ksize
+        pm = np.zeros(n, dtype=np.uint64)
+        pk = np.zeros(self.dim(True), dtype=np.uint64)
+        cnt = C.c_uint64()
+        _lib.check(self._lib.ktb_oligo_pos_maps(self._h, pm.ctypes.data, pk.ctypes.data, C.byref(cnt)))
+        return pm, pk, int(cnt.value)
+
+    def set_option(self, key: str, value: int) -> None:
+        _lib.check(self._lib.ktb_oligo_set_option(self._h, key.encode(), int(value)))
+
+    def stats(self) -> dict:
+        st = _lib.Stats()
+        _lib.check(self._lib.ktb_oligo_last_stats(self._h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def vectorise_batch_array(self, seqs: Sequence, norm: bool = True, mins: bool = True,
+                              dtype=np.float64) -> np.ndarray:
+        bases, offsets = _pack(seqs)
+        return self.vectorise_packed(bases, offsets, norm_mode=NORM_PY if norm else NORM_COUNTS, mins=mins,
+                                     dtype=dtype)
+
+    def vectorise_packed(self, bases: np.ndarray, offsets: np.ndarray, norm_mode: int = NORM_CLI,
+                         mins: bool = True, dtype=np.float32, out: np.ndarray | None = None,
+                         totals: np.ndarray | None = None) -> np.ndarray:
+        """Rows for sequences bases[offsets[i]:offsets[i+1]] (host buffers, chunked H2D/compute/D2H)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        d = self.dim(mins)
+        code = _CODES[np.dtype(dtype)]
+        if out is None:
+            out = np.empty((n, d), dtype=_DTYPES[code])
+        assert out.shape == (n, d) and out.dtype == _DTYPES[code] and out.flags.c_contiguous
+        tptr = None
+        if totals is not None:
+            assert totals.dtype == np.uint64 and totals.shape == (n,) and totals.flags.c_contiguous
+            tptr = totals.ctypes.data
+        bptr = bases.ctypes.data if bases.size else None
+        _lib.check(self._lib.ktb_oligo_vectorise(self._h, bptr, offsets.ctypes.data, n, int(mins), int(norm_mode),
+                                                 code, out.ctypes.data if n else None, tptr))
+        return out
+
+    def vectorise_device(self, d_bases: int, d_offsets: int, n: int, total_bases: int, d_out: int,
+                         norm_mode: int = NORM_CLI, mins: bool = True, out_dtype: int = OUT_F32,
+                         d_totals: int | None = None, stream: int | None = None) -> None:
+        """Device-pointer entry point (raw addresses, e.g. torch.Tensor.data_ptr()); asynchronous."""
+        _lib.check(self._lib.ktb_oligo_vectorise_device(self._h, d_bases, d_offsets, n, total_bases, int(mins),
+                                                        int(norm_mode), int(out_dtype), d_out, d_totals, stream))

@@ -1,0 +1,60 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/kmertools_b200.h
+declares, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from kmertools_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "kmertools_b200.h").read_text()
+    declared = set(re.findall(r"\b(ktb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ktb_oligo", "ktb_stats"}
+    assert declared, "no declarations parsed"
+    L = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SYMBOLS), "ctypes table and header disagree"
+    assert L.ktb_abi_version() == 1
+
+
+def test_library_is_standalone():
+    """cudart is linked statically: the only CUDA dependency is the driver (loaded lazily)."""
+    import subprocess
+    out = subprocess.run(["ldd", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "libcudart" not in out and "libtorch" not in out and "oracle" not in out
+
+
+def test_product_never_references_the_oracle():
+    """The oracle is test infrastructure: no product source may import, link or even mention it."""
+    files = list((ROOT / "kmertools_b200").rglob("*.py")) + list((ROOT / "pykmertools").rglob("*.py")) + \
+        [p for p in (ROOT / "kmertools_b200" / "csrc").glob("*") if p.is_file()]
+    assert files
+    for p in files:
+        assert "oracle" not in p.read_text(errors="ignore").lower(), p
+
+
+def test_argument_errors_without_gpu():
+    L = _lib.load()
+    h = C.c_void_p()
+    assert L.ktb_oligo_create(0, 0, C.byref(h)) == _lib.KTB_ERR_ARG
+    assert L.ktb_oligo_create(13, 0, C.byref(h)) == _lib.KTB_ERR_ARG
+    assert b"k must be" in L.ktb_last_error()
+    if L.ktb_device_count() == 0:
+        assert L.ktb_oligo_create(4, 0, C.byref(h)) == _lib.KTB_ERR_NODEVICE
+        assert b"no CPU path" in L.ktb_last_error()
+        from kmertools_b200 import OligoComputer, KtbError
+        with pytest.raises(KtbError):
+            OligoComputer(4)
+
+
+def test_utils_mirror():  # tests/test_utils.py of the reference
+    from pykmertools import utils
+    assert utils.to_acgt(111, 5) == "ACGTT"
+    assert utils.to_numeric("ACGTT") == (111, 27)

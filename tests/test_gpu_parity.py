@@ -1,0 +1,198 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Needs a B200: -m gpu."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import assert_rows_equal, random_batch
+
+pytestmark = pytest.mark.gpu
+
+from kmertools_b200 import OligoComputer  # noqa: E402
+from kmertools_b200._lib import NORM_CLI, NORM_COUNTS, NORM_PY  # noqa: E402
+
+_cache = {}
+
+
+def comp(k):
+    if k not in _cache:
+        _cache[k] = OligoComputer(k)
+    return _cache[k]
+
+
+def check(k, bases, offsets, mins=True, norm_mode=NORM_CLI, dtype=np.float32, what="", **opts):
+    oc = comp(k)
+    for key in ("force_path", "short_variant"):
+        oc.set_option(key, opts.get(key, 0))
+    n = len(offsets) - 1
+    totals = np.zeros(n, dtype=np.uint64)
+    got = oc.vectorise_packed(bases, offsets, norm_mode=norm_mode, mins=mins, dtype=dtype, totals=totals)
+    want, wtot = O.vectorise_batch(bases, offsets, k, mins, norm_mode)
+    assert np.array_equal(totals, wtot), f"{what}: totals differ"
+    assert_rows_equal(got, want, dtype, what)
+    for key in ("force_path", "short_variant"):
+        oc.set_option(key, 0)
+    return got
+
+
+def test_nt4_table_matches_reference_table():
+    import ctypes as C
+    from kmertools_b200 import _lib
+    oc = comp(4)
+    buf = (C.c_uint8 * 256)()
+    _lib.check(oc._lib.ktb_debug_nt4_table(oc._h, buf))
+    assert list(buf) == [O.nt4(b) for b in range(256)]
+
+
+@pytest.mark.parametrize("fname", ["reads.fa", "reads.fq", "reads.fq.gz"])
+def test_golden_files(golden, fname):
+    """Config 1: k=4 canonical normalised on the repo fixture, byte-equal text after formatting."""
+    seqs = [s for _, s in O.read_fastx(golden / fname)]
+    bases, offsets = O.pack(seqs)
+    rows = check(4, bases, offsets, dtype=np.float64, what=fname)
+    assert O.format_rows(rows, True) == (golden / "expected_fa.kmers").read_bytes()
+    cnt = check(4, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32)
+    assert O.format_rows(cnt.astype(np.float64), False) == (golden / "expected_fa_batch_unnorm.kmers").read_bytes()
+
+
+def test_python_api_golden(golden):
+    """tests/test_oligo.py of the reference, unmodified logic, against pykmertools drop-in."""
+    import pykmertools as kt
+    oligo_gen = kt.OligoComputer(4)
+    seqs = [s.decode() for _, s in O.read_fastx(golden / "reads.fq")]
+    gen = [[round(x, 6) for x in line] for line in oligo_gen.vectorise_batch(seqs)]
+    truth = [list(map(float, ln.split())) for ln in (golden / "expected_fa.kmers").read_text().splitlines()]
+    assert gen == truth
+    assert len(oligo_gen.get_header()) == 136 and len(oligo_gen.get_header(False)) == 256
+    assert oligo_gen.get_header() == O.header(4, True)
+    one = oligo_gen.vectorise_one(seqs[0])
+    assert one == oligo_gen.vectorise_batch(seqs)[0]
+    raw = oligo_gen.vectorise_one(seqs[0], True, False)
+    assert abs(sum(raw) - 0.5) < 1e-12  # the reference's raw-mode quirk
+
+
+def test_unit_kats():
+    oc = comp(4)
+    v = oc.vectorise_batch_array([b"AAAANGAGA"], True, True)
+    assert v[0, 0] == 0.5
+    u = oc.vectorise_batch_array([b"AAAANGAGA"], False, True)
+    assert u[0, 0] == 1.0 and u.sum() == 2.0
+    z = oc.vectorise_batch_array([b"ACG", b"", b"NNNNNNNN"], True, True)
+    assert not z.any()
+    a = oc.vectorise_batch_array([b"acgu", b"ACGT", bytes([0, 1, 2, 3]), b"ACGTRACGT"], False, True)
+    assert a[0].tolist() == a[1].tolist() == a[2].tolist() and a[0, 27] == 1 and a[0].sum() == 1
+    assert a[3].sum() == 2
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("mins", [True, False])
+def test_short_reads_all_k(k, mins):
+    rng = np.random.default_rng(100 + k)
+    lengths = rng.integers(0, 300, size=700)
+    bases, offsets = random_batch(rng, lengths, noise=0.02)
+    if k == 8 and not mins:
+        lengths = lengths[:64]
+        bases, offsets = random_batch(rng, lengths, noise=0.02)
+    check(k, bases, offsets, mins=mins, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"k{k} counts")
+    check(k, bases, offsets, mins=mins, norm_mode=NORM_CLI, dtype=np.float32, what=f"k{k} f32")
+    check(k, bases, offsets, mins=mins, norm_mode=NORM_PY, dtype=np.float64, what=f"k{k} f64 py")
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_short_kernel_variants_uniform_150(variant):
+    rng = np.random.default_rng(5)
+    bases, offsets = random_batch(rng, np.full(5000, 150), noise=0.001)
+    for k in (3, 4, 5):
+        check(k, bases, offsets, dtype=np.float32, short_variant=variant, what=f"150bp k{k} v{variant}")
+        check(k, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, short_variant=variant)
+
+
+@pytest.mark.parametrize("k", [3, 4, 5, 6, 7, 8])
+def test_medium_and_long_sequences(k):
+    rng = np.random.default_rng(200 + k)
+    lengths = np.r_[rng.integers(300, 5000, size=40), rng.integers(20000, 120000, size=6), [0, 1, k - 1, k, k + 1]]
+    bases, offsets = random_batch(rng, lengths, noise=0.001, n_runs=0.5)
+    check(k, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"k{k} counts")
+    check(k, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, what=f"k{k} f32")
+    check(k, bases, offsets, mins=False, norm_mode=NORM_CLI, dtype=np.float64, what=f"k{k} raw f64") if k < 8 else None
+
+
+@pytest.mark.parametrize("k", [9, 10])
+def test_large_k_global_path(k):
+    rng = np.random.default_rng(300 + k)
+    lengths = np.r_[rng.integers(0, 3000, size=12), [50000]]
+    bases, offsets = random_batch(rng, lengths, noise=0.002, n_runs=0.3)
+    check(k, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"k{k} counts")
+    check(k, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, what=f"k{k} f32")
+    if k == 9:
+        check(k, bases, offsets, norm_mode=NORM_CLI, dtype=np.float64, what=f"k{k} f64")
+
+
+@pytest.mark.parametrize("k", [3, 5, 7])
+def test_forced_global_path_matches(k):
+    rng = np.random.default_rng(400 + k)
+    lengths = rng.integers(0, 2000, size=200)
+    bases, offsets = random_batch(rng, lengths, noise=0.01)
+    check(k, bases, offsets, dtype=np.float32, force_path=1, what="global path")
+    check(k, bases, offsets, dtype=np.float32, force_path=2, what="no short kernel")
+
+
+def test_mixed_short_and_long_groups():
+    """Short groups, ineligible groups and long contigs interleaved (length-binned dispatch)."""
+    rng = np.random.default_rng(9)
+    lengths = np.r_[np.full(64, 150), [100000], np.full(40, 100), rng.integers(0, 3000, size=50), np.full(33, 259)]
+    bases, offsets = random_batch(rng, lengths, noise=0.005, n_runs=0.2)
+    for k in (4, 5):
+        check(k, bases, offsets, dtype=np.float32, what=f"mixed k{k}")
+        check(k, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"mixed k{k}")
+
+
+def test_chunked_host_pipeline_matches():
+    rng = np.random.default_rng(11)
+    bases, offsets = random_batch(rng, rng.integers(100, 200, size=20000), noise=0.001)
+    oc = comp(5)
+    oc.set_option("chunk_bytes", 1 << 20)  # ~40 chunks
+    try:
+        check(5, bases, offsets, dtype=np.float32, what="chunked")
+        st = oc.stats()
+        assert st["launches"] >= 40 and st["d2h_bytes"] >= 20000 * 512 * 4
+    finally:
+        oc.set_option("chunk_bytes", 512 << 20)
+
+
+def test_survey_hashes_via_gpu(golden):
+    """sha256 of the CLI text for k=3..7 x {canonical,raw} x {norm,counts}."""
+    from tests.test_oracle import SURVEY_KATS
+    seqs = [s for _, s in O.read_fastx(golden / "reads.fa")]
+    bases, offsets = O.pack(seqs)
+    for k, want in SURVEY_KATS.items():
+        got = []
+        for mins in (True, False):
+            for norm in (True, False):
+                rows = comp(k).vectorise_packed(bases, offsets, norm_mode=NORM_CLI if norm else NORM_COUNTS,
+                                                mins=mins, dtype=np.float64)
+                got.append(hashlib.sha256(O.format_rows(rows, norm)).hexdigest()[:16])
+        assert tuple(got) == want, k
+
+
+def test_device_entry_point_with_torch_tensors():
+    import torch
+    rng = np.random.default_rng(12)
+    bases, offsets = random_batch(rng, np.full(4096, 150), noise=0.001)
+    oc = comp(5)
+    dev = torch.device("cuda:0")
+    tb = torch.from_numpy(bases).to(dev)
+    to = torch.from_numpy(offsets.astype(np.int64)).to(dev)
+    out = torch.empty((4096, 512), dtype=torch.float32, device=dev)
+    tot = torch.zeros(4096, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream()
+    oc.vectorise_device(tb.data_ptr(), to.data_ptr(), 4096, int(offsets[-1]), out.data_ptr(),
+                        d_totals=tot.data_ptr(), stream=st.cuda_stream)
+    st.synchronize()
+    want, wtot = O.vectorise_batch(bases, offsets, 5, True, NORM_CLI)
+    assert_rows_equal(out.cpu().numpy(), want, np.float32, "device path")
+    assert np.array_equal(tot.cpu().numpy().astype(np.uint64), wtot)
+    # size-independent property: every row sums to 1 (or 0)
+    s = out.sum(dim=1)
+    assert torch.all((s - 1).abs() < 1e-4)
