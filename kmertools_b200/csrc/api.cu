@@ -95,10 +95,10 @@ struct ktb_oligo {
     // device tables
     uint32_t *d_rank_full = nullptr;       // [4^k] any code -> rank of its canonical form
     uint32_t *d_canon_of_rank = nullptr;   // [dim_canon padded to 4]
-    uint16_t *d_short_tab_canon = nullptr; // [4^k] (k <= 5)
-    uint16_t *d_short_tab_raw = nullptr;
+    uint32_t *d_short_tab_canon = nullptr; // [4^k] (k <= 5): (word byte offset << 22) | 8*(bin&3)
+    uint32_t *d_short_tab_raw = nullptr;
     unsigned long long *d_counters = nullptr;  // [4]
-    DevBuf ws_totals, ws_counts;
+    DevBuf ws_totals, ws_counts, ws_list;
     ChunkSet sets[NBUF];
     int sm_count = 0;
     size_t smem_optin = 0;
@@ -127,42 +127,35 @@ int set_smem(K kern, size_t bytes) {
 
 struct ShortCfg {
     bool ok = false;
-    uint32_t words = 0, stage_bytes = 0, max_len = 0;
-    int warps = 0;
+    uint32_t words = 0, max_len = 0;
     size_t smem = 0;
 };
+
+constexpr int SHORT_WARPS = 8;
 
 ShortCfg short_config(const ktb_oligo *h, uint64_t dim) {
     ShortCfg c;
     if (h->ncodes > (uint64_t)SHORT_MAX_CODES || (dim & 3) || h->force_path != 0) return c;
     c.words = (uint32_t)(dim / 4);
     c.max_len = 254u + (uint32_t)h->k;
-    c.stage_bytes = ((32u * c.max_len + 16u + 15u) / 16u) * 16u;
-    if (c.stage_bytes < 32u * 33u * 4u) c.stage_bytes = 32u * 33u * 4u;
-    const size_t per_warp = (size_t)c.words * 128u + c.stage_bytes;
-    const size_t avail = h->smem_optin - 4096;  // static tables + slack
-    int warps = (int)(avail / per_warp);
-    if (warps > 16) warps = 16;
-    if (h->short_warps > 0 && h->short_warps < warps) warps = h->short_warps;
-    if (warps < 1) return c;
-    c.warps = warps;
-    c.smem = per_warp * (size_t)warps;
-    c.ok = true;
+    c.smem = (size_t)SHORT_WARPS * ((size_t)SHORT_G * c.words + 32) * 4;
+    c.ok = c.smem + 8192 <= h->smem_optin;
     return c;
 }
 
 template <int OUT>
 int launch_short(ktb_oligo *h, const ShortParams &p, const ShortCfg &c, cudaStream_t st) {
-    auto kern = h->short_variant ? short_kernel<OUT, true> : short_kernel<OUT, false>;
+    auto kern = short_kernel<OUT>;
     if (int rc = set_smem(kern, c.smem)) return rc;
     int per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, c.warps * 32, c.smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SHORT_WARPS * 32, c.smem));
     if (per_sm < 1) per_sm = 1;
+    if (h->short_warps > 0) per_sm = std::min(per_sm, std::max(1, h->short_warps / SHORT_WARPS));
     uint64_t grid = (uint64_t)h->sm_count * per_sm;
-    const uint64_t need = (p.ngroups + c.warps - 1) / c.warps;
+    const uint64_t need = (p.ngroups + SHORT_WARPS - 1) / SHORT_WARPS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, c.warps * 32, c.smem, st>>>(p);
+    kern<<<(unsigned)grid, SHORT_WARPS * 32, c.smem, st>>>(p);
     CU(cudaGetLastError());
     h->stats.launches++;
     return KTB_OK;
@@ -180,7 +173,7 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)h->sm_count * per_sm;
-    const uint64_t ngroups = (p.n + 31) / 32;
+    const uint64_t ngroups = (p.n + p.group_size - 1) / p.group_size;
     if (grid > ngroups) grid = ngroups;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, 256, smem, st>>>(p);
@@ -214,15 +207,21 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
     if (hist_mode >= 0) {
         CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
         const ShortCfg sc = short_config(h, dim);
+        const uint64_t ngroups = (n + SHORT_G - 1) / SHORT_G;
         if (sc.ok) {
+            if (int rc = h->ws_list.ensure(ngroups * 4)) return rc;
             ShortParams sp{};
-            sp.bases = d_bases; sp.offsets = d_offsets; sp.n = n; sp.ngroups = (n + 31) / 32;
+            sp.bases = d_bases; sp.offsets = d_offsets; sp.n = n; sp.ngroups = ngroups;
+            sp.total_bases = total_bases;
             sp.out = d_out; sp.totals = d_totals;
             sp.tab = canonical ? h->d_short_tab_canon : h->d_short_tab_raw;
             sp.counter = h->d_counters + 0;
+            sp.reject_list = (uint32_t *)h->ws_list.p;
+            sp.reject_count = h->d_counters + 2;
             sp.k = h->k; sp.ncodes = (uint32_t)h->ncodes; sp.dim = (uint32_t)dim; sp.words = sc.words;
-            sp.stage_bytes = sc.stage_bytes; sp.max_len = sc.max_len;
-            sp.norm_mode = norm_mode; sp.canonical = canonical; sp.warps = sc.warps;
+            sp.words_recip = sc.words > 1 ? (uint32_t)(0xFFFFFFFFu / sc.words + 1u) : 0u;
+            sp.max_len = sc.max_len;
+            sp.norm_mode = norm_mode; sp.canonical = canonical;
             if (int rc = launch_short<OUT>(h, sp, sc, st)) return rc;
         }
         SeqParams qp{};
@@ -232,7 +231,9 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         qp.counter = h->d_counters + 1;
         qp.k = h->k; qp.dim = (uint32_t)dim; qp.hist_entries = (uint32_t)hist_entries;
         qp.norm_mode = norm_mode; qp.canonical = canonical;
-        qp.skip_short = sc.ok ? 1 : 0; qp.short_max_len = sc.max_len; qp.short_stage_bytes = sc.stage_bytes;
+        qp.list = sc.ok ? (const uint32_t *)h->ws_list.p : nullptr;
+        qp.list_count = sc.ok ? h->d_counters + 2 : nullptr;
+        qp.group_size = SHORT_G;
         return launch_seq<OUT>(h, qp, hist_mode, st);
     }
 
@@ -382,16 +383,16 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
     CUB(cudaMalloc(&h->d_canon_of_rank, cor.size() * 4));
     CUB(cudaMemcpy(h->d_canon_of_rank, cor.data(), cor.size() * 4, cudaMemcpyHostToDevice));
     if (h->ncodes <= (uint64_t)ktb::SHORT_MAX_CODES) {
-        std::vector<uint16_t> tc(h->ncodes), tr(h->ncodes);
+        std::vector<uint32_t> tc(h->ncodes), tr(h->ncodes);
         for (uint64_t x = 0; x < h->ncodes; ++x) {
             const uint32_t a = rank_full[x], b = (uint32_t)x;
-            tc[x] = (uint16_t)((a >> 2) * 128u + (a & 3u));
-            tr[x] = (uint16_t)((b >> 2) * 128u + (b & 3u));
+            tc[x] = ((a & ~3u) << 22) | ((a & 3u) * 8u);
+            tr[x] = ((b & ~3u) << 22) | ((b & 3u) * 8u);
         }
-        CUB(cudaMalloc(&h->d_short_tab_canon, h->ncodes * 2));
-        CUB(cudaMalloc(&h->d_short_tab_raw, h->ncodes * 2));
-        CUB(cudaMemcpy(h->d_short_tab_canon, tc.data(), h->ncodes * 2, cudaMemcpyHostToDevice));
-        CUB(cudaMemcpy(h->d_short_tab_raw, tr.data(), h->ncodes * 2, cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_short_tab_canon, h->ncodes * 4));
+        CUB(cudaMalloc(&h->d_short_tab_raw, h->ncodes * 4));
+        CUB(cudaMemcpy(h->d_short_tab_canon, tc.data(), h->ncodes * 4, cudaMemcpyHostToDevice));
+        CUB(cudaMemcpy(h->d_short_tab_raw, tr.data(), h->ncodes * 4, cudaMemcpyHostToDevice));
     }
     CUB(cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)));
     for (auto &s : h->sets) {
@@ -420,6 +421,7 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     }
     h->ws_totals.release();
     h->ws_counts.release();
+    h->ws_list.release();
     if (h->d_rank_full) cudaFree(h->d_rank_full);
     if (h->d_canon_of_rank) cudaFree(h->d_canon_of_rank);
     if (h->d_short_tab_canon) cudaFree(h->d_short_tab_canon);

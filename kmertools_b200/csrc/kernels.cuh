@@ -79,179 +79,8 @@ __device__ __forceinline__ typename OutT<OUT>::type make_out(uint32_t cnt, bool 
 }
 
 // ================================================================================================
-// short_kernel — thread per read
+// shared decode helpers (16 bases per lane from one 128-bit word group)
 // ================================================================================================
-struct ShortParams {
-    const uint8_t *bases;
-    const uint64_t *offsets;
-    uint64_t n;
-    uint64_t ngroups;        // ceil(n / 32)
-    void *out;
-    uint64_t *totals;        // optional
-    const uint16_t *tab;     // [4^k] code -> byte offset of its bin inside a lane's histogram
-    unsigned long long *counter;  // dynamic group counter (zeroed before launch)
-    uint32_t k;
-    uint32_t ncodes;         // 4^k  (<= 1024)
-    uint32_t dim;            // row width, multiple of 4
-    uint32_t words;          // dim / 4 : 32-bit histogram words per read
-    uint32_t stage_bytes;    // per-warp staging buffer, multiple of 16, >= 32*33*4
-    uint32_t max_len;        // longest read this kernel takes: 254 + k
-    int norm_mode;
-    int canonical;
-    int warps;               // warps per CTA
-};
-
-constexpr int SHORT_MAX_CODES = 1024;
-
-// Histogram layout (per warp): word w of lane t lives at hist[w * 32 + t], so every lane only ever
-// touches bank t: the scattered increments of the accumulate phase are bank-conflict free without
-// atomics.  Counts are bytes (<= 255 windows per read), four bins per word, and one word converts
-// to exactly one 128-bit store of four floats on the way out.
-template <int OUT, bool ATOM>
-__global__ void __launch_bounds__(512, 1) short_kernel(const ShortParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint16_t s_tab[SHORT_MAX_CODES];
-    __shared__ uint8_t s_lut[256];
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < p.ncodes; i += blockDim.x) s_tab[i] = p.tab[i];
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = (uint8_t)nt4_code(i);
-
-    const uint32_t hist_bytes = p.words * 128u;
-    uint8_t *my = smem + (size_t)warp * (hist_bytes + p.stage_bytes);
-    uint32_t *hist = reinterpret_cast<uint32_t *>(my);
-    uint8_t *stage = my + hist_bytes;
-    for (uint32_t i = lane; i < p.words * 32u; i += 32) hist[i] = 0;
-    __syncthreads();
-
-    const uint32_t kmask = (p.k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * p.k)) - 1u);
-    using T = typename OutT<OUT>::type;
-    T *out = reinterpret_cast<T *>(p.out);
-    const bool norm = p.norm_mode != NORM_COUNTS;
-
-    for (;;) {
-        unsigned long long g = 0;
-        if (lane == 0) g = atomicAdd(p.counter, 1ULL);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        if (g >= p.ngroups) break;
-        const uint64_t i0 = g * 32ULL;
-        const uint64_t i = i0 + lane;
-        const uint64_t o0 = (i <= p.n) ? p.offsets[i] : p.offsets[p.n];
-        const uint64_t o1 = (i + 1 <= p.n) ? p.offsets[i + 1] : o0;
-        const uint32_t len = (uint32_t)min((unsigned long long)(o1 - o0), 0xFFFFFFFFULL);
-        const uint64_t span0 = __shfl_sync(0xffffffffu, o0, 0) & ~15ULL;  // 16B-aligned span start
-        const uint64_t span1 = __shfl_sync(0xffffffffu, o1, 31);
-        // group eligibility: every read short enough for byte counters, span fits the stage buffer
-        const bool ok = __all_sync(0xffffffffu, len <= p.max_len) &&
-                        (span1 - span0 + 16 <= p.stage_bytes);
-        if (!ok) continue;  // seq_kernel takes this group
-
-        // ---- stage the group's bases (coalesced 128-bit loads; tail bytewise)
-        const uint64_t nbytes = span1 - span0;
-        const uint64_t nvec = nbytes >> 4;
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.bases + span0);
-        uint4 *dst = reinterpret_cast<uint4 *>(stage);
-        for (uint64_t v = lane; v < nvec; v += 32) dst[v] = __ldg(src + v);
-        for (uint64_t b = (nvec << 4) + lane; b < nbytes; b += 32) stage[b] = p.bases[span0 + b];
-        __syncwarp();
-
-        // ---- accumulate: each lane walks its own read
-        const uint32_t sb = (uint32_t)(o0 - span0);
-        const uint32_t a = sb & 3u;
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(stage) + (sb >> 2);
-        const uint32_t nwords = (len == 0) ? 0u : ((a + len + 3u) >> 2);
-        uint32_t maxwords = nwords;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) maxwords = max(maxwords, __shfl_xor_sync(0xffffffffu, maxwords, s));
-        uint8_t *hb = my + lane * 4;
-        uint32_t f = 0, run = 0, tot = 0;
-        for (uint32_t wi = 0; wi < maxwords; ++wi) {
-            const uint32_t w = (wi < nwords) ? wp[wi] : 0xFFFFFFFFu;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t pos = wi * 4u + j - a;  // wraps for the bytes before the read
-                const uint32_t b = (w >> (8 * j)) & 0xFFu;
-                uint32_t c = s_lut[b];
-                c = (pos < len) ? c : 4u;
-                f = ((f << 2) | (c & 3u)) & kmask;
-                run = (c < 4u) ? run + 1u : 0u;
-                if (run >= p.k) {
-                    const uint32_t off = s_tab[f];
-                    if constexpr (ATOM) {
-                        atomicAdd(reinterpret_cast<uint32_t *>(hb + (off & 0xFFFCu)), 1u << ((off & 3u) * 8u));
-                    } else {
-                        hb[off] = (uint8_t)(hb[off] + 1u);
-                    }
-                    ++tot;
-                }
-            }
-        }
-        if (p.totals && i < p.n) p.totals[i] = tot;
-        __syncwarp();
-
-        // ---- write-out: 32x32 word transposes through the (now free) stage buffer, zeroing as we go
-        uint32_t *tr = reinterpret_cast<uint32_t *>(stage);  // [32][33]
-        const uint64_t dv = norm_divisor(tot, p.norm_mode, p.canonical);
-        const float dF = (float)dv;
-        const float rinv = __frcp_rn(dF);
-        for (uint32_t wb = 0; wb < p.words; wb += 32) {
-            const uint32_t nw = min(32u, p.words - wb);
-            for (uint32_t j = 0; j < nw; ++j) {
-                const uint32_t v = hist[(wb + j) * 32u + lane];
-                hist[(wb + j) * 32u + lane] = 0;
-                tr[lane * 33 + j] = v;
-            }
-            __syncwarp();
-            const uint32_t nreads = (uint32_t)min((unsigned long long)32, (unsigned long long)(p.n - i0));
-            for (uint32_t r = 0; r < nreads; ++r) {
-                const float dFr = __shfl_sync(0xffffffffu, dF, r);
-                const float rinvr = __shfl_sync(0xffffffffu, rinv, r);
-                if (lane < nw) {
-                    const uint32_t v = tr[r * 33 + lane];
-                    T *dstp = out + (i0 + r) * (uint64_t)p.dim + (uint64_t)(wb + lane) * 4u;
-                    const double dD = (double)dFr;
-                    T e0 = make_out<OUT>(v & 0xFFu, norm, true, dFr, rinvr, dD);
-                    T e1 = make_out<OUT>((v >> 8) & 0xFFu, norm, true, dFr, rinvr, dD);
-                    T e2 = make_out<OUT>((v >> 16) & 0xFFu, norm, true, dFr, rinvr, dD);
-                    T e3 = make_out<OUT>(v >> 24, norm, true, dFr, rinvr, dD);
-                    if constexpr (OUT == OUT_F64) {
-                        reinterpret_cast<double2 *>(dstp)[0] = make_double2(e0, e1);
-                        reinterpret_cast<double2 *>(dstp)[1] = make_double2(e2, e3);
-                    } else if constexpr (OUT == OUT_F32) {
-                        *reinterpret_cast<float4 *>(dstp) = make_float4(e0, e1, e2, e3);
-                    } else {
-                        *reinterpret_cast<uint4 *>(dstp) = make_uint4(e0, e1, e2, e3);
-                    }
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
-// ================================================================================================
-// seq_kernel — CTA per sequence, shared-memory atomics
-// ================================================================================================
-struct SeqParams {
-    const uint8_t *bases;        // 16-byte aligned
-    const uint64_t *offsets;
-    uint64_t n;
-    uint64_t total_bases;
-    void *out;
-    uint64_t *totals;            // optional
-    const uint32_t *rank_full;   // [4^k] code -> rank of its canonical form (rank-space mode)
-    const uint32_t *canon_of_rank;  // [dim] rank -> canonical code       (code-space mode)
-    unsigned long long *counter; // dynamic group counter (zeroed before launch)
-    uint32_t k;
-    uint32_t dim;
-    uint32_t hist_entries;       // shared-memory histogram entries (4^k in code space, dim in rank space)
-    int norm_mode;
-    int canonical;
-    int skip_short;              // 1: groups that short_kernel accepts are skipped here
-    uint32_t short_max_len;
-    uint32_t short_stage_bytes;
-};
 
 // 16 bases -> packed 2-bit codes (base j at bits 2*(15-j)+1..2*(15-j), oldest base most significant)
 // and a 16-bit validity mask (base j at bit 15-j).
@@ -294,19 +123,273 @@ __device__ __forceinline__ uint32_t revcomp_pack(uint32_t cf) {
     return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
 }
 
+// bit b of the result is set <=> bits b..b+k-1 of V are all set (older bases = higher bits)
+__device__ __forceinline__ uint32_t window_mask(uint32_t V, uint32_t k) {
+    uint32_t vw = V, have = 1;
+    while (have < k) {
+        const uint32_t step = min(have, k - have);
+        vw &= vw >> step;
+        have += step;
+    }
+    return vw;
+}
+
+// 16 bytes at p (16-byte aligned offset into bases) without touching memory at or beyond `total`
+__device__ __forceinline__ uint4 load16_guarded(const uint8_t *bases, uint64_t p, uint64_t total) {
+    if (p + 16 <= total) return __ldg(reinterpret_cast<const uint4 *>(bases + p));
+    uint32_t t[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    for (uint64_t b = p; b < total; ++b) {
+        const uint32_t sh = (uint32_t)(b - p);
+        t[sh >> 2] = (t[sh >> 2] & ~(0xFFu << ((sh & 3) * 8))) | ((uint32_t)bases[b] << ((sh & 3) * 8));
+    }
+    return make_uint4(t[0], t[1], t[2], t[3]);
+}
+
+// ================================================================================================
+// short_kernel — one warp per group of G consecutive short reads, 16 bases per lane per step
+// ================================================================================================
+struct ShortParams {
+    const uint8_t *bases;     // 16-byte aligned
+    const uint64_t *offsets;
+    uint64_t n;
+    uint64_t ngroups;         // ceil(n / G)
+    uint64_t total_bases;
+    void *out;
+    uint64_t *totals;         // optional
+    const uint32_t *tab;      // [4^k] code -> (byte offset of the bin's word << 22) | (8 * (bin & 3))
+    unsigned long long *counter;        // dynamic group counter (zeroed before launch)
+    uint32_t *reject_list;              // groups this kernel does not take (consumed by seq_kernel)
+    unsigned long long *reject_count;   // zeroed before launch
+    uint32_t k;
+    uint32_t ncodes;          // 4^k  (<= 1024)
+    uint32_t dim;             // row width, multiple of 4
+    uint32_t words;           // dim / 4 : 32-bit histogram words per read (4 byte counters each)
+    uint32_t words_recip;     // ceil(2^32 / words)
+    uint32_t max_len;         // longest read this kernel takes: 254 + k (<= 255 windows fit a byte)
+    int norm_mode;
+    int canonical;
+};
+
+constexpr int SHORT_MAX_CODES = 1024;
+constexpr int SHORT_G = 16;   // reads per warp-group
+
+// Work decomposition: the reads of a group are cut into read-aligned 16-base chunks; chunk t of the
+// group goes to lane t%32 of step t/32, so all 16 windows a lane emits belong to one read and one
+// histogram.  A lane fetches its (unaligned) 16 bytes with two aligned 128-bit loads and a byte funnel,
+// turns them into a 2-bit packed word + validity mask, gets the previous chunk's word from its
+// neighbour lane by shuffle (look-back for windows straddling chunks) and cuts the k-mers out of the
+// 64-bit window.  Counters are bytes packed four to a word (a short read has <= 255 windows), updated
+// with shared-memory atomics (measured 13-15 random updates/cycle/SM, profiles/r1_microbench*.txt).
+// Write-out walks the group's histograms linearly: one word -> four floats -> one 128-bit store.
+template <int OUT>
+__global__ void __launch_bounds__(256) short_kernel(const ShortParams p) {
+    extern __shared__ __align__(16) uint32_t smem_u32[];
+    __shared__ uint32_t s_tab[SHORT_MAX_CODES];
+
+    constexpr int G = SHORT_G;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < p.ncodes; i += blockDim.x) s_tab[i] = p.tab[i];
+
+    const uint32_t hwords = G * p.words;                    // histogram words per warp
+    uint32_t *hist = smem_u32 + (size_t)warp * (hwords + 32);
+    uint32_t *s_tot = hist + hwords;                        // [G] valid windows per read (+pad)
+    for (uint32_t i = lane; i < hwords + 32; i += 32) hist[i] = 0;
+    __syncthreads();
+
+    const uint32_t k = p.k;
+    const uint32_t kmask = (1u << (2 * k)) - 1u;
+    using T = typename OutT<OUT>::type;
+    T *out = reinterpret_cast<T *>(p.out);
+    const bool norm = p.norm_mode != NORM_COUNTS;
+    constexpr uint32_t FULL = 0xffffffffu;
+
+    for (;;) {
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(p.counter, 1ULL);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= p.ngroups) break;
+        const uint64_t i0 = g * (uint64_t)G;
+        const uint32_t nreads = (uint32_t)min((unsigned long long)G, (unsigned long long)(p.n - i0));
+        // lane j < nreads owns read i0+j
+        uint64_t o0 = 0, o1 = 0;
+        if ((uint32_t)lane < nreads) {
+            o0 = p.offsets[i0 + lane];
+            o1 = p.offsets[i0 + lane + 1];
+        }
+        const uint64_t lenl = o1 - o0;
+        if (!__all_sync(FULL, lenl <= (uint64_t)p.max_len)) {
+            if (lane == 0) p.reject_list[atomicAdd(p.reject_count, 1ULL)] = (uint32_t)g;
+            continue;
+        }
+        const uint32_t len = (uint32_t)lenl;
+        const uint64_t gbase = __shfl_sync(FULL, o0, 0);
+        const uint32_t rel = (uint32_t)(o0 - gbase);        // start of my read relative to the group
+        const uint32_t cnt = (len + 15u) >> 4;              // 16-base chunks in my read
+        uint32_t cum = cnt;                                 // inclusive prefix sum over lanes
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, cum, s);
+            if (lane >= s) cum += v;
+        }
+        const uint32_t ex = cum - cnt;                      // first chunk index of my read
+        const uint32_t ntasks = __shfl_sync(FULL, cum, 31);
+        const uint32_t len0 = __shfl_sync(FULL, len, 0);
+        const bool uniform = __all_sync(FULL, (uint32_t)lane >= nreads || len == len0) && len0 > 0;
+        const uint32_t cpr = (len0 + 15u) >> 4;
+        const uint32_t cpr_recip = uniform ? (0xFFFFFFFFu / cpr + 1u) : 0u;
+
+        uint32_t carry_cf = 0, carry_vm = 0;
+        for (uint32_t t0 = 0; t0 < ntasks; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            const bool active = t < ntasks;
+            // ---- which read / which chunk of it
+            uint32_t r, q;
+            if (uniform) {
+                r = (cpr == 1) ? t : __umulhi(t, cpr_recip);
+                q = t - r * cpr;
+            } else {
+                r = 0;
+                uint32_t exr = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {  // largest r with ex[r] <= t
+                    const uint32_t cand = r + s;
+                    const uint32_t v = __shfl_sync(FULL, ex, cand & 31);
+                    if (cand < nreads && v <= t) { r = cand; exr = v; }
+                }
+                q = t - exr;
+            }
+            r = active ? r : 0;
+            const uint32_t rrel = __shfl_sync(FULL, rel, r);
+            const uint32_t rlen = __shfl_sync(FULL, len, r);
+            uint32_t cf = 0, vm = 0;
+            if (active) {
+                const uint64_t addr = gbase + rrel + 16u * q;
+                const uint32_t nvalid = min(16u, rlen - 16u * q);
+                const uint32_t a = (uint32_t)addr & 15u;
+                const uint64_t pa = addr - a;
+                const uint4 v0 = load16_guarded(p.bases, pa, p.total_bases);
+                uint4 u = v0;
+                if (a) {
+                    uint4 v1 = make_uint4(0, 0, 0, 0);
+                    if (a + nvalid > 16u) v1 = load16_guarded(p.bases, pa + 16, p.total_bases);
+                    // byte funnel: u = bytes a..a+15 of (v0 : v1)
+                    uint32_t W0 = v0.x, W1 = v0.y, W2 = v0.z, W3 = v0.w, W4 = v1.x, W5 = v1.y, W6 = v1.z, W7 = v1.w;
+                    if (a & 8u) { W0 = W2; W1 = W3; W2 = W4; W3 = W5; W4 = W6; W5 = W7; }
+                    if (a & 4u) { W0 = W1; W1 = W2; W2 = W3; W3 = W4; W4 = W5; }
+                    const uint32_t bs = (a & 3u) * 8u;
+                    u.x = __funnelshift_r(W0, W1, bs);
+                    u.y = __funnelshift_r(W1, W2, bs);
+                    u.z = __funnelshift_r(W2, W3, bs);
+                    u.w = __funnelshift_r(W3, W4, bs);
+                }
+                decode16(u, cf, vm);
+                vm &= (0xFFFF0000u >> nvalid) & 0xFFFFu;   // bases past the end of the read
+            }
+            uint32_t cf_prev = __shfl_up_sync(FULL, cf, 1);
+            uint32_t vm_prev = __shfl_up_sync(FULL, vm, 1);
+            if (lane == 0) { cf_prev = carry_cf; vm_prev = carry_vm; }
+            carry_cf = __shfl_sync(FULL, cf, 31);
+            carry_vm = __shfl_sync(FULL, vm, 31);
+            if (q == 0) vm_prev = 0;                       // first chunk of a read: no look-back
+            const uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
+            if (active && vw) {
+                atomicAdd(&s_tot[r], (uint32_t)__popc(vw));
+                const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
+                uint8_t *hb = reinterpret_cast<uint8_t *>(hist + r * p.words);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (vw & (1u << (15 - j))) {
+                        const uint32_t f = (uint32_t)(F64 >> (2 * (15 - j))) & kmask;
+                        const uint32_t e = s_tab[f];
+                        atomicAdd(reinterpret_cast<uint32_t *>(hb + (e >> 22)), 1u << (e & 31u));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- write-out: linear sweep over the group's histograms (rows are contiguous in `out`)
+        if (p.totals && (uint32_t)lane < nreads) p.totals[i0 + lane] = s_tot[lane];
+        T *obase = out + i0 * (uint64_t)p.dim;
+        const uint32_t nw = nreads * p.words;
+        for (uint32_t i = lane; i < nw; i += 32) {
+            const uint32_t r = (p.words == 1u) ? i : __umulhi(i, p.words_recip);
+            const uint32_t v = hist[i];
+            const uint64_t dv = norm_divisor(s_tot[r], p.norm_mode, p.canonical);
+            const float dF = (float)dv;
+            const float rinv = __frcp_rn(dF);
+            const double dD = (double)dv;
+            // byte -> float without I2F: 0x4B000000 | b is the float 2^23 + b
+            T e0, e1, e2, e3;
+            if constexpr (OUT == OUT_F32) {
+                const float c0 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440)) - 8388608.0f;
+                const float c1 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7441)) - 8388608.0f;
+                const float c2 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7442)) - 8388608.0f;
+                const float c3 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7443)) - 8388608.0f;
+                e0 = norm ? quot_f32(c0, dF, rinv) : c0;
+                e1 = norm ? quot_f32(c1, dF, rinv) : c1;
+                e2 = norm ? quot_f32(c2, dF, rinv) : c2;
+                e3 = norm ? quot_f32(c3, dF, rinv) : c3;
+            } else {
+                e0 = make_out<OUT>(v & 0xFFu, norm, true, dF, rinv, dD);
+                e1 = make_out<OUT>((v >> 8) & 0xFFu, norm, true, dF, rinv, dD);
+                e2 = make_out<OUT>((v >> 16) & 0xFFu, norm, true, dF, rinv, dD);
+                e3 = make_out<OUT>(v >> 24, norm, true, dF, rinv, dD);
+            }
+            T *dstp = obase + (uint64_t)i * 4u;
+            if constexpr (OUT == OUT_F64) {
+                reinterpret_cast<double2 *>(dstp)[0] = make_double2(e0, e1);
+                reinterpret_cast<double2 *>(dstp)[1] = make_double2(e2, e3);
+            } else if constexpr (OUT == OUT_F32) {
+                *reinterpret_cast<float4 *>(dstp) = make_float4(e0, e1, e2, e3);
+            } else {
+                *reinterpret_cast<uint4 *>(dstp) = make_uint4(e0, e1, e2, e3);
+            }
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < nw + 32; i += 32) hist[(i < nw) ? i : (hwords + i - nw)] = 0;
+        __syncwarp();
+    }
+}
+
+// ================================================================================================
+// seq_kernel — CTA per sequence, shared-memory atomics
+// ================================================================================================
+struct SeqParams {
+    const uint8_t *bases;        // 16-byte aligned
+    const uint64_t *offsets;
+    uint64_t n;
+    uint64_t total_bases;
+    void *out;
+    uint64_t *totals;            // optional
+    const uint32_t *rank_full;   // [4^k] code -> rank of its canonical form (rank-space mode)
+    const uint32_t *canon_of_rank;  // [dim] rank -> canonical code       (code-space mode)
+    unsigned long long *counter; // dynamic group counter (zeroed before launch)
+    uint32_t k;
+    uint32_t dim;
+    uint32_t hist_entries;       // shared-memory histogram entries (4^k in code space, dim in rank space)
+    int norm_mode;
+    int canonical;
+    const uint32_t *list;        // groups to process (short_kernel's rejects); nullptr = every group
+    const unsigned long long *list_count;
+    uint32_t group_size;         // sequences per group (SHORT_G)
+};
+
 // HIST_MODE: 0 = raw (index f), 1 = canonical code space (index min(f,r), gather on write-out),
 //            2 = canonical rank space (index rank_full[f], linear write-out)
 template <int OUT, int HIST_MODE>
 __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
     extern __shared__ __align__(16) uint32_t hist[];
     __shared__ unsigned long long s_group;
-    __shared__ int s_skip;
     __shared__ uint32_t s_total[2];  // double-buffered so the reset never races a late reader
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
+    const uint64_t nitems = p.list ? (uint64_t)*p.list_count : (p.n + p.group_size - 1) / p.group_size;
+    if ((uint64_t)blockIdx.x >= nitems) return;  // nothing for this CTA (e.g. short_kernel took everything)
     for (uint32_t i = tid; i < p.hist_entries; i += blockDim.x) hist[i] = 0;
     if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
     __syncthreads();
@@ -317,31 +400,17 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
     using T = typename OutT<OUT>::type;
     T *out = reinterpret_cast<T *>(p.out);
     const bool norm = p.norm_mode != NORM_COUNTS;
-    const uint64_t ngroups = (p.n + 31) / 32;
     const bool vec_ok = (p.dim & 3u) == 0;
 
     for (;;) {
         if (tid == 0) s_group = atomicAdd(p.counter, 1ULL);
         __syncthreads();
-        const unsigned long long g = s_group;
-        if (g >= ngroups) break;
-        const uint64_t i0 = g * 32ULL;
-        if (warp == 0) {
-            int skip = 0;
-            if (p.skip_short) {
-                const uint64_t i = i0 + lane;
-                const uint64_t o0 = (i <= p.n) ? p.offsets[i] : p.offsets[p.n];
-                const uint64_t o1 = (i + 1 <= p.n) ? p.offsets[i + 1] : o0;
-                const uint64_t span0 = __shfl_sync(0xffffffffu, o0, 0) & ~15ULL;
-                const uint64_t span1 = __shfl_sync(0xffffffffu, o1, 31);
-                skip = __all_sync(0xffffffffu, (o1 - o0) <= p.short_max_len) &&
-                       (span1 - span0 + 16 <= p.short_stage_bytes);
-            }
-            if (lane == 0) s_skip = skip;
-        }
-        __syncthreads();
-        if (s_skip) continue;
-        const uint32_t nseq = (uint32_t)min((unsigned long long)32, (unsigned long long)(p.n - i0));
+        const unsigned long long item = s_group;
+        __syncthreads();  // everyone has read s_group before tid 0 overwrites it next round
+        if (item >= nitems) break;
+        const uint64_t g = p.list ? (uint64_t)p.list[item] : (uint64_t)item;
+        const uint64_t i0 = g * (uint64_t)p.group_size;
+        const uint32_t nseq = (uint32_t)min((unsigned long long)p.group_size, (unsigned long long)(p.n - i0));
 
         for (uint32_t si = 0; si < nseq; ++si) {
             const uint64_t seq = i0 + si;

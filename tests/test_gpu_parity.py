@@ -99,13 +99,44 @@ def test_short_reads_all_k(k, mins):
     check(k, bases, offsets, mins=mins, norm_mode=NORM_PY, dtype=np.float64, what=f"k{k} f64 py")
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-def test_short_kernel_variants_uniform_150(variant):
+@pytest.mark.parametrize("length", [150, 100, 16, 17, 31, 250, 259])
+def test_short_kernel_uniform_lengths(length):
     rng = np.random.default_rng(5)
-    bases, offsets = random_batch(rng, np.full(5000, 150), noise=0.001)
+    bases, offsets = random_batch(rng, np.full(3001, length), noise=0.001)
     for k in (3, 4, 5):
-        check(k, bases, offsets, dtype=np.float32, short_variant=variant, what=f"150bp k{k} v{variant}")
-        check(k, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, short_variant=variant)
+        check(k, bases, offsets, dtype=np.float32, what=f"{length}bp k{k}")
+        check(k, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"{length}bp k{k} counts")
+    check(5, bases, offsets, mins=False, norm_mode=NORM_PY, dtype=np.float64, what=f"{length}bp raw f64")
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_short_kernel_ragged_and_tiny_reads(k):
+    """Everything short-eligible: tiny reads (< 16 bp, several per 16-base chunk), empties, N runs,
+    homopolymers that push a byte counter to its 255 limit."""
+    rng = np.random.default_rng(50 + k)
+    lengths = np.r_[rng.integers(0, 40, size=500), rng.integers(0, 255 + k, size=1500), [254 + k] * 40, [0] * 20]
+    rng.shuffle(lengths)
+    bases, offsets = random_batch(rng, lengths, noise=0.02, n_runs=0.1)
+    # homopolymer reads of the maximum short length: one bin reaches 255
+    for i in range(0, 2000, 97):
+        bases[int(offsets[i]):int(offsets[i + 1])] = ord("A")
+    for mins in (True, False):
+        check(k, bases, offsets, mins=mins, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"ragged k{k} counts")
+        check(k, bases, offsets, mins=mins, norm_mode=NORM_CLI, dtype=np.float32, what=f"ragged k{k} f32")
+    check(k, bases, offsets, norm_mode=NORM_PY, dtype=np.float64, what=f"ragged k{k} f64")
+    st = comp(k).stats()
+    assert st["launches"] >= 1
+
+
+def test_unaligned_base_pointer_phase():
+    """Host path keeps the caller's 16-byte phase: start the batch at every offset 0..15."""
+    rng = np.random.default_rng(77)
+    bases, offsets = random_batch(rng, np.full(200, 150), noise=0.001)
+    for shift in range(16):
+        pad = np.frombuffer(b"G" * shift, dtype=np.uint8)
+        b2 = np.concatenate([pad, bases])
+        o2 = offsets + np.uint64(shift)
+        check(5, b2, o2, dtype=np.float32, what=f"phase {shift}")
 
 
 @pytest.mark.parametrize("k", [3, 4, 5, 6, 7, 8])
