@@ -138,14 +138,14 @@ ShortCfg short_config(const ktb_oligo *h, uint64_t dim) {
     if (h->ncodes > (uint64_t)SHORT_MAX_CODES || (dim & 3) || h->force_path != 0) return c;
     c.words = (uint32_t)(dim / 4);
     c.max_len = 254u + (uint32_t)h->k;
-    c.smem = (size_t)SHORT_WARPS * ((size_t)SHORT_G * c.words + 32) * 4;
+    c.smem = (size_t)SHORT_WARPS * ((size_t)SHORT_G * c.words + SHORT_PAD) * 4;
     c.ok = c.smem + 8192 <= h->smem_optin;
     return c;
 }
 
 template <int OUT>
 int launch_short(ktb_oligo *h, const ShortParams &p, const ShortCfg &c, cudaStream_t st) {
-    auto kern = short_kernel<OUT>;
+    auto kern = (p.norm_mode != NORM_COUNTS) ? short_kernel<OUT, true> : short_kernel<OUT, false>;
     if (int rc = set_smem(kern, c.smem)) return rc;
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SHORT_WARPS * 32, c.smem));

@@ -137,7 +137,7 @@ __device__ __forceinline__ uint32_t window_mask(uint32_t V, uint32_t k) {
 // 16 bytes at p (16-byte aligned offset into bases) without touching memory at or beyond `total`
 __device__ __forceinline__ uint4 load16_guarded(const uint8_t *bases, uint64_t p, uint64_t total) {
     if (p + 16 <= total) return __ldg(reinterpret_cast<const uint4 *>(bases + p));
-    uint32_t t[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    uint32_t t[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};  // filler decodes on the fast path
     for (uint64_t b = p; b < total; ++b) {
         const uint32_t sh = (uint32_t)(b - p);
         t[sh >> 2] = (t[sh >> 2] & ~(0xFFu << ((sh & 3) * 8))) | ((uint32_t)bases[b] << ((sh & 3) * 8));
@@ -172,6 +172,7 @@ struct ShortParams {
 
 constexpr int SHORT_MAX_CODES = 1024;
 constexpr int SHORT_G = 16;   // reads per warp-group
+constexpr int SHORT_PAD = 64;  // per-warp scratch words after the histograms (totals, divisors)
 
 // Work decomposition: the reads of a group are cut into read-aligned 16-base chunks; chunk t of the
 // group goes to lane t%32 of step t/32, so all 16 windows a lane emits belong to one read and one
@@ -181,7 +182,7 @@ constexpr int SHORT_G = 16;   // reads per warp-group
 // 64-bit window.  Counters are bytes packed four to a word (a short read has <= 255 windows), updated
 // with shared-memory atomics (measured 13-15 random updates/cycle/SM, profiles/r1_microbench*.txt).
 // Write-out walks the group's histograms linearly: one word -> four floats -> one 128-bit store.
-template <int OUT>
+template <int OUT, bool NORM>
 __global__ void __launch_bounds__(256) short_kernel(const ShortParams p) {
     extern __shared__ __align__(16) uint32_t smem_u32[];
     __shared__ uint32_t s_tab[SHORT_MAX_CODES];
@@ -192,16 +193,17 @@ __global__ void __launch_bounds__(256) short_kernel(const ShortParams p) {
     for (uint32_t i = threadIdx.x; i < p.ncodes; i += blockDim.x) s_tab[i] = p.tab[i];
 
     const uint32_t hwords = G * p.words;                    // histogram words per warp
-    uint32_t *hist = smem_u32 + (size_t)warp * (hwords + 32);
-    uint32_t *s_tot = hist + hwords;                        // [G] valid windows per read (+pad)
-    for (uint32_t i = lane; i < hwords + 32; i += 32) hist[i] = 0;
+    uint32_t *hist = smem_u32 + (size_t)warp * (hwords + SHORT_PAD);
+    uint32_t *s_tot = hist + hwords;                        // [G] valid windows per read
+    float *s_df = reinterpret_cast<float *>(s_tot + G);     // [G] divisor as float
+    float *s_ri = reinterpret_cast<float *>(s_tot + 2 * G); // [G] RN(1 / divisor)
+    for (uint32_t i = lane; i < hwords + SHORT_PAD; i += 32) hist[i] = 0;
     __syncthreads();
 
     const uint32_t k = p.k;
-    const uint32_t kmask = (1u << (2 * k)) - 1u;
+    const uint32_t kmask4 = ((1u << (2 * k)) - 1u) << 2;   // k-mer code pre-scaled to a byte offset into s_tab
     using T = typename OutT<OUT>::type;
     T *out = reinterpret_cast<T *>(p.out);
-    const bool norm = p.norm_mode != NORM_COUNTS;
     constexpr uint32_t FULL = 0xffffffffu;
 
     for (;;) {
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(256) short_kernel(const ShortParams p) {
                 const uint4 v0 = load16_guarded(p.bases, pa, p.total_bases);
                 uint4 u = v0;
                 if (a) {
-                    uint4 v1 = make_uint4(0, 0, 0, 0);
+                    uint4 v1 = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
                     if (a + nvalid > 16u) v1 = load16_guarded(p.bases, pa + 16, p.total_bases);
                     // byte funnel: u = bytes a..a+15 of (v0 : v1)
                     uint32_t W0 = v0.x, W1 = v0.y, W2 = v0.z, W3 = v0.w, W4 = v1.x, W5 = v1.y, W6 = v1.z, W7 = v1.w;
@@ -293,49 +295,62 @@ __global__ void __launch_bounds__(256) short_kernel(const ShortParams p) {
             carry_vm = __shfl_sync(FULL, vm, 31);
             if (q == 0) vm_prev = 0;                       // first chunk of a read: no look-back
             const uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
-            if (active && vw) {
-                atomicAdd(&s_tot[r], (uint32_t)__popc(vw));
-                const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
-                uint8_t *hb = reinterpret_cast<uint8_t *>(hist + r * p.words);
+            if (vw) atomicAdd(&s_tot[r], (uint32_t)__popc(vw));
+            // all 16 table look-ups first (independent, pipelined), then the atomics
+            const uint64_t F4 = (((uint64_t)cf_prev << 32) | cf) << 2;
+            uint8_t *hb = reinterpret_cast<uint8_t *>(hist + r * p.words);
+            uint32_t e[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (vw & (1u << (15 - j))) {
-                        const uint32_t f = (uint32_t)(F64 >> (2 * (15 - j))) & kmask;
-                        const uint32_t e = s_tab[f];
-                        atomicAdd(reinterpret_cast<uint32_t *>(hb + (e >> 22)), 1u << (e & 31u));
-                    }
-                }
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t idx4 = (uint32_t)(F4 >> (2 * (15 - j))) & kmask4;
+                e[j] = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(s_tab) + idx4);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                // branch-free: an invalid window adds 0 (ptxas turns a predicated ATOMS into a branch)
+                const uint32_t one = (vw >> (15 - j)) & 1u;
+                atomicAdd(reinterpret_cast<uint32_t *>(hb + (e[j] >> 22)), one << (e[j] & 31u));
             }
         }
         __syncwarp();
 
         // ---- write-out: linear sweep over the group's histograms (rows are contiguous in `out`)
-        if (p.totals && (uint32_t)lane < nreads) p.totals[i0 + lane] = s_tot[lane];
+        if ((uint32_t)lane < nreads) {
+            const uint32_t tot = s_tot[lane];
+            if (p.totals) p.totals[i0 + lane] = tot;
+            const float dF = (float)norm_divisor(tot, p.norm_mode, p.canonical);  // <= 510, exact
+            s_df[lane] = dF;
+            s_ri[lane] = __frcp_rn(dF);
+        }
+        __syncwarp();
         T *obase = out + i0 * (uint64_t)p.dim;
         const uint32_t nw = nreads * p.words;
         for (uint32_t i = lane; i < nw; i += 32) {
             const uint32_t r = (p.words == 1u) ? i : __umulhi(i, p.words_recip);
             const uint32_t v = hist[i];
-            const uint64_t dv = norm_divisor(s_tot[r], p.norm_mode, p.canonical);
-            const float dF = (float)dv;
-            const float rinv = __frcp_rn(dF);
-            const double dD = (double)dv;
-            // byte -> float without I2F: 0x4B000000 | b is the float 2^23 + b
+            const float dF = s_df[r];
+            const float rinv = s_ri[r];
             T e0, e1, e2, e3;
-            if constexpr (OUT == OUT_F32) {
+            if constexpr (OUT == OUT_U32) {
+                e0 = v & 0xFFu; e1 = (v >> 8) & 0xFFu; e2 = (v >> 16) & 0xFFu; e3 = v >> 24;
+            } else {
+                // byte -> float without I2F: 0x4B000000 | b is the float 2^23 + b
                 const float c0 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440)) - 8388608.0f;
                 const float c1 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7441)) - 8388608.0f;
                 const float c2 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7442)) - 8388608.0f;
                 const float c3 = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7443)) - 8388608.0f;
-                e0 = norm ? quot_f32(c0, dF, rinv) : c0;
-                e1 = norm ? quot_f32(c1, dF, rinv) : c1;
-                e2 = norm ? quot_f32(c2, dF, rinv) : c2;
-                e3 = norm ? quot_f32(c3, dF, rinv) : c3;
-            } else {
-                e0 = make_out<OUT>(v & 0xFFu, norm, true, dF, rinv, dD);
-                e1 = make_out<OUT>((v >> 8) & 0xFFu, norm, true, dF, rinv, dD);
-                e2 = make_out<OUT>((v >> 16) & 0xFFu, norm, true, dF, rinv, dD);
-                e3 = make_out<OUT>(v >> 24, norm, true, dF, rinv, dD);
+                if constexpr (OUT == OUT_F32) {
+                    e0 = NORM ? quot_f32(c0, dF, rinv) : c0;
+                    e1 = NORM ? quot_f32(c1, dF, rinv) : c1;
+                    e2 = NORM ? quot_f32(c2, dF, rinv) : c2;
+                    e3 = NORM ? quot_f32(c3, dF, rinv) : c3;
+                } else {
+                    const double dD = (double)dF;
+                    e0 = NORM ? (double)c0 / dD : (double)c0;
+                    e1 = NORM ? (double)c1 / dD : (double)c1;
+                    e2 = NORM ? (double)c2 / dD : (double)c2;
+                    e3 = NORM ? (double)c3 / dD : (double)c3;
+                }
             }
             T *dstp = obase + (uint64_t)i * 4u;
             if constexpr (OUT == OUT_F64) {
@@ -348,7 +363,10 @@ __global__ void __launch_bounds__(256) short_kernel(const ShortParams p) {
             }
         }
         __syncwarp();
-        for (uint32_t i = lane; i < nw + 32; i += 32) hist[(i < nw) ? i : (hwords + i - nw)] = 0;
+        {
+            uint4 *hz = reinterpret_cast<uint4 *>(hist);
+            for (uint32_t i = lane; i < (hwords + SHORT_PAD) / 4; i += 32) hz[i] = make_uint4(0, 0, 0, 0);
+        }
         __syncwarp();
     }
 }
