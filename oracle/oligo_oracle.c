@@ -289,3 +289,26 @@ int64_t ktb_oracle_format_row(const double *row, uint64_t dim, int norm, const c
     buf[w] = 0;
     return (int64_t)w;
 }
+
+/* Checker for the GPU's f32 normalisation (kmertools_b200/csrc/kernels.cuh quot_f32): the same
+ * three-operation sequence in C — q0 = c*RN(1/d); rem = fma(-q0,d,c); q = fma(rem,RN(1/d),q0) — must
+ * equal (float)((double)c/(double)d), the reference's f64 quotient rounded once, for every
+ * 0 <= c <= d, dlo <= d <= dhi.  Returns the number of mismatches. */
+#include <math.h>
+uint64_t ktb_oracle_check_quot_f32(uint32_t dlo, uint32_t dhi, uint32_t cstep) {
+    uint64_t bad = 0;
+    if (cstep == 0) cstep = 1;
+    for (uint32_t d = dlo; d <= dhi; d++) {
+        const float df = (float)d;
+        const float rinv = 1.0f / df;
+        for (uint32_t c = 0; c <= d; c += cstep) {
+            const float cf = (float)c;
+            const float q0 = cf * rinv;
+            const float rem = fmaf(-q0, df, cf);
+            const float q = fmaf(rem, rinv, q0);
+            const float want = (float)((double)c / (double)d);
+            if (q != want) bad++;
+        }
+    }
+    return bad;
+}

@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         L.ktb_oracle_format_row.restype = C.c_int64
         L.ktb_oracle_format_row.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_char_p, C.c_char_p,
                                             C.c_uint64]
+        L.ktb_oracle_check_quot_f32.restype = C.c_uint64
+        L.ktb_oracle_check_quot_f32.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         _ = (u8p, f64p)
         _lib = L
     return _lib
@@ -165,6 +167,11 @@ def baseline_batch(bases: np.ndarray, offsets: np.ndarray, k: int, canonical: bo
     cs = lib().ktb_oracle_baseline_batch(bases.ctypes.data, offsets.ctypes.data, n, k, int(canonical),
                                          norm_mode, threads, C.byref(used))
     return float(cs), int(used.value)
+
+
+def check_quot_f32(dlo: int, dhi: int, cstep: int = 1) -> int:
+    """Mismatches of the GPU's f32 division sequence vs (float)(f64 quotient) over a divisor range."""
+    return int(lib().ktb_oracle_check_quot_f32(dlo, dhi, cstep))
 
 
 def max_threads() -> int:

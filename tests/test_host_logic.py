@@ -1,0 +1,29 @@
+"""CPU-side checks of host logic and of arithmetic claims the kernels rely on."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def test_f32_division_sequence_is_correctly_rounded():
+    """q0 = c*RN(1/d); q = fma(fma(-q0,d,c), RN(1/d), q0) == (float)((double)c/(double)d).
+    Exhaustive for every divisor a short read (<= 510) or a 4 kbp sequence can produce, sampled above."""
+    assert O.check_quot_f32(1, 4096, 1) == 0
+    assert O.check_quot_f32(4097, 70000, 997) == 0
+    assert O.check_quot_f32((1 << 24) - 300, (1 << 24) - 1, 65537) == 0
+
+
+def test_bench_algorithmic_bytes_formula():
+    import bench
+    # config 2 = 22.06 GB, config 3 = 42.78 GB
+    assert bench.algorithmic_bytes(1_500_000_000, 10_000_000, 512, 4) == 22_060_000_008
+    assert abs(bench.algorithmic_bytes(10_000_000_000, 1_000_000, 8192, 4) - 42.78e9) < 0.01e9
+    assert [bench.dim_of(k) for k in (3, 4, 5, 6, 7, 8, 10)] == [32, 136, 512, 2080, 8192, 32896, 524800]
+
+
+def test_pack_helper_matches_oracle_pack():
+    from kmertools_b200.oligo import _pack
+    seqs = ["ACGT", "", "NNACGTTT", "acgu"]
+    b1, o1 = _pack(seqs)
+    b2, o2 = O.pack([s.encode() for s in seqs])
+    assert np.array_equal(b1, b2) and np.array_equal(o1, o2)
