@@ -165,9 +165,10 @@ template <int OUT>
 int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st) {
     const size_t smem = (size_t)p.hist_entries * 4;
     void (*kern)(const SeqParams) = nullptr;
-    if (hist_mode == 0) kern = seq_kernel<OUT, 0>;
-    else if (hist_mode == 1) kern = seq_kernel<OUT, 1>;
-    else kern = seq_kernel<OUT, 2>;
+    const bool nrm = p.norm_mode != NORM_COUNTS;
+    if (hist_mode == 0) kern = nrm ? seq_kernel<OUT, 0, true> : seq_kernel<OUT, 0, false>;
+    else if (hist_mode == 1) kern = nrm ? seq_kernel<OUT, 1, true> : seq_kernel<OUT, 1, false>;
+    else kern = nrm ? seq_kernel<OUT, 2, true> : seq_kernel<OUT, 2, false>;
     if (int rc = set_smem(kern, smem)) return rc;
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));

@@ -396,7 +396,24 @@ struct SeqParams {
 
 // HIST_MODE: 0 = raw (index f), 1 = canonical code space (index min(f,r), gather on write-out),
 //            2 = canonical rank space (index rank_full[f], linear write-out)
-template <int OUT, int HIST_MODE>
+// count -> output element; counts < 2^23 become floats through the 2^23 magic constant (no I2F)
+template <int OUT, bool NORM>
+__device__ __forceinline__ typename OutT<OUT>::type cvt_count(uint32_t cnt, bool small_div, float dF,
+                                                              float rinv, double dD) {
+    if constexpr (OUT == OUT_U32) {
+        return cnt;
+    } else if constexpr (OUT == OUT_F32) {
+        if (small_div) {  // then also cnt < 2^24
+            const float c = (cnt < (1u << 23)) ? __uint_as_float(0x4B000000u | cnt) - 8388608.0f : (float)cnt;
+            return NORM ? quot_f32(c, dF, rinv) : c;
+        }
+        return NORM ? (float)((double)cnt / dD) : (float)cnt;
+    } else {
+        return NORM ? (double)cnt / dD : (double)cnt;
+    }
+}
+
+template <int OUT, int HIST_MODE, bool NORM>
 __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
     extern __shared__ __align__(16) uint32_t hist[];
     __shared__ unsigned long long s_group;
@@ -417,8 +434,8 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
     const uint32_t kmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
     using T = typename OutT<OUT>::type;
     T *out = reinterpret_cast<T *>(p.out);
-    const bool norm = p.norm_mode != NORM_COUNTS;
     const bool vec_ok = (p.dim & 3u) == 0;
+    constexpr uint32_t FULL = 0xffffffffu;
 
     for (;;) {
         if (tid == 0) s_group = atomicAdd(p.counter, 1ULL);
@@ -440,73 +457,63 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
                 // its warp's first emitting chunk as look-back, so a warp advances 31 chunks per step
                 const int64_t c_first = (int64_t)(s0 >> 4);
                 const int64_t c_last = (int64_t)((s1 - 1) >> 4);
-                for (int64_t cb = c_first + (int64_t)warp * 31; cb <= c_last; cb += (int64_t)nwarps * 31) {
+                const int64_t stride = (int64_t)nwarps * 31;
+                int64_t cb = c_first + (int64_t)warp * 31;
+                const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+                auto fetch = [&](int64_t cbase) -> uint4 {
+                    const int64_t c = cbase + lane - 1;
+                    if (c >= c_first && c <= c_last) return load16_guarded(p.bases, (uint64_t)c << 4, p.total_bases);
+                    return filler;
+                };
+                uint4 vnext = (cb <= c_last) ? fetch(cb) : filler;
+                for (; cb <= c_last; cb += stride) {
+                    const uint4 v = vnext;
+                    if (cb + stride <= c_last) vnext = fetch(cb + stride);  // prefetch the next strip
                     const int64_t c = cb + lane - 1;
-                    uint32_t cf = 0, vm = 0;
-                    if (c >= c_first && c <= c_last) {
-                        const uint64_t a = (uint64_t)c << 4;
-                        uint4 v;
-                        if (a + 16 <= p.total_bases) {
-                            v = __ldg(reinterpret_cast<const uint4 *>(p.bases + a));
-                        } else {
-                            uint32_t t[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-                            for (uint64_t b = a; b < p.total_bases; ++b) {
-                                const uint32_t sh = (uint32_t)(b - a);
-                                t[sh >> 2] = (t[sh >> 2] & ~(0xFFu << ((sh & 3) * 8))) |
-                                             ((uint32_t)p.bases[b] << ((sh & 3) * 8));
-                            }
-                            v = make_uint4(t[0], t[1], t[2], t[3]);
-                        }
-                        decode16(v, cf, vm);
-                        // keep only bases inside [s0, s1)
-                        const uint32_t lo = (s0 > a) ? (uint32_t)(s0 - a) : 0u;
-                        const uint32_t hi = (s1 - a < 16) ? (uint32_t)(s1 - a) : 16u;
-                        const uint32_t rm = ((1u << (16 - lo)) - 1u) & ~((1u << (16 - hi)) - 1u);
+                    uint32_t cf, vm;
+                    decode16(v, cf, vm);
+                    {   // keep only bases inside [s0, s1)
+                        const int64_t a = c << 4;
+                        const int64_t lo64 = (int64_t)s0 - a, hi64 = (int64_t)s1 - a;
+                        const uint32_t lo = lo64 > 0 ? (lo64 < 16 ? (uint32_t)lo64 : 16u) : 0u;
+                        const uint32_t hi = hi64 < 16 ? (hi64 > 0 ? (uint32_t)hi64 : 0u) : 16u;
+                        const uint32_t rm = (0xFFFFu >> lo) & ~(0xFFFFu >> hi);
                         vm &= rm;
                     }
-                    const uint32_t cf_prev = __shfl_up_sync(0xffffffffu, cf, 1);
-                    const uint32_t vm_prev = __shfl_up_sync(0xffffffffu, vm, 1);
-                    if (lane == 0 || vm == 0) continue;  // lane 0 only supplies look-back
+                    const uint32_t cf_prev = __shfl_up_sync(FULL, cf, 1);
+                    const uint32_t vm_prev = __shfl_up_sync(FULL, vm, 1);
                     // windows: bit b of vw set <=> V32 bits b..b+k-1 all set (older bases = higher bits)
-                    const uint32_t V32 = (vm_prev << 16) | vm;
-                    uint32_t vw = V32;
-                    {
-                        uint32_t have = 1;
-                        while (have < k) {
-                            const uint32_t step = min(have, k - have);
-                            vw &= vw >> step;
-                            have += step;
-                        }
-                    }
-                    vw &= 0xFFFFu;
-                    if (vw == 0) continue;
+                    uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
+                    if (lane == 0) vw = 0;  // lane 0 only supplies look-back
                     mine += __popc(vw);
                     const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
                     uint64_t R64 = 0;
                     if constexpr (HIST_MODE == 1) {
                         R64 = ((uint64_t)revcomp_pack(cf) << 32) | revcomp_pack(cf_prev);
                     }
+                    uint32_t idx[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        if (vw & (1u << (15 - j))) {
-                            const uint32_t f = (uint32_t)(F64 >> (2 * (15 - j))) & kmask;
-                            uint32_t idx;
-                            if constexpr (HIST_MODE == 0) {
-                                idx = f;
-                            } else if constexpr (HIST_MODE == 1) {
-                                const uint32_t r = (uint32_t)(R64 >> (2 * (17 + j - (int)k))) & kmask;
-                                idx = min(f, r);
-                            } else {
-                                idx = __ldg(p.rank_full + f);
-                            }
-                            atomicAdd(&hist[idx], 1u);
+                        const uint32_t f = (uint32_t)(F64 >> (2 * (15 - j))) & kmask;
+                        if constexpr (HIST_MODE == 0) {
+                            idx[j] = f;
+                        } else if constexpr (HIST_MODE == 1) {
+                            const uint32_t r = (uint32_t)(R64 >> (2 * (17 + j - (int)k))) & kmask;
+                            idx[j] = min(f, r);
+                        } else {
+                            idx[j] = __ldg(p.rank_full + f);
                         }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        // branch-free: an invalid window adds 0
+                        atomicAdd(&hist[idx[j]], (vw >> (15 - j)) & 1u);
                     }
                 }
             }
             // ---- total = block sum of `mine`
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, s);
+            for (int s = 16; s > 0; s >>= 1) mine += __shfl_xor_sync(FULL, mine, s);
             if (lane == 0 && mine) atomicAdd(&s_total[it & 1], mine);
             __syncthreads();
             const uint32_t total = s_total[it & 1];
@@ -532,10 +539,10 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
                         cnt[0] = hv.x; cnt[1] = hv.y; cnt[2] = hv.z; cnt[3] = hv.w;
                         *reinterpret_cast<uint4 *>(hist + j) = make_uint4(0, 0, 0, 0);
                     }
-                    T e0 = make_out<OUT>(cnt[0], norm, small_div, dF, rinv, dD);
-                    T e1 = make_out<OUT>(cnt[1], norm, small_div, dF, rinv, dD);
-                    T e2 = make_out<OUT>(cnt[2], norm, small_div, dF, rinv, dD);
-                    T e3 = make_out<OUT>(cnt[3], norm, small_div, dF, rinv, dD);
+                    T e0 = cvt_count<OUT, NORM>(cnt[0], small_div, dF, rinv, dD);
+                    T e1 = cvt_count<OUT, NORM>(cnt[1], small_div, dF, rinv, dD);
+                    T e2 = cvt_count<OUT, NORM>(cnt[2], small_div, dF, rinv, dD);
+                    T e3 = cvt_count<OUT, NORM>(cnt[3], small_div, dF, rinv, dD);
                     if constexpr (OUT == OUT_F64) {
                         reinterpret_cast<double2 *>(row + j)[0] = make_double2(e0, e1);
                         reinterpret_cast<double2 *>(row + j)[1] = make_double2(e2, e3);
@@ -556,7 +563,7 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
                         cnt = hist[j];
                         hist[j] = 0;
                     }
-                    row[j] = make_out<OUT>(cnt, norm, small_div, dF, rinv, dD);
+                    row[j] = cvt_count<OUT, NORM>(cnt, small_div, dF, rinv, dD);
                 }
             }
             __syncthreads();
