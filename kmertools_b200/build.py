@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
     LIBDIR.mkdir(exist_ok=True)
-    cmd = [nvcc(), *NVCC_FLAGS]
+    cmd = [nvcc(), *NVCC_FLAGS, *os.environ.get("KTB_NVCC_EXTRA", "").split()]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", str(LIB), *map(str, sources())]

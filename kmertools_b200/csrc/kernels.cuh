@@ -21,6 +21,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef KTB_SEQ_FASTPATH
+#define KTB_SEQ_FASTPATH 0
+#endif
+
 namespace ktb {
 
 constexpr int OUT_U32 = 0, OUT_F32 = 1, OUT_F64 = 2;
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(256) short_kernel(const ShortParams p) {
             r = active ? r : 0;
             const uint32_t rrel = __shfl_sync(FULL, rel, r);
             const uint32_t rlen = __shfl_sync(FULL, len, r);
-            uint32_t cf = 0, vm = 0;
+            uint32_t cf = (uint32_t)lane * 0x9E3779B1u, vm = 0;  // idle lanes add 0 at scattered bins
             if (active) {
                 const uint64_t addr = gbase + rrel + 16u * q;
                 const uint32_t nvalid = min(16u, rlen - 16u * q);
@@ -396,23 +400,74 @@ struct SeqParams {
 
 // HIST_MODE: 0 = raw (index f), 1 = canonical code space (index min(f,r), gather on write-out),
 //            2 = canonical rank space (index rank_full[f], linear write-out)
-// count -> output element; counts < 2^23 become floats through the 2^23 magic constant (no I2F)
-template <int OUT, bool NORM>
-__device__ __forceinline__ typename OutT<OUT>::type cvt_count(uint32_t cnt, bool small_div, float dF,
-                                                              float rinv, double dD) {
+// count -> output element.  SMALL: every count (and the divisor) is below 2^23, so the float comes
+// from the 2^23 magic constant (no quarter-rate I2F) and the exact f32 division sequence applies.
+template <int OUT, bool NORM, bool SMALL>
+__device__ __forceinline__ typename OutT<OUT>::type cvt_count(uint32_t cnt, float dF, float rinv, double dD) {
     if constexpr (OUT == OUT_U32) {
         return cnt;
     } else if constexpr (OUT == OUT_F32) {
-        if (small_div) {  // then also cnt < 2^24
-            const float c = (cnt < (1u << 23)) ? __uint_as_float(0x4B000000u | cnt) - 8388608.0f : (float)cnt;
+        if constexpr (SMALL) {
+            const float c = __uint_as_float(0x4B000000u | cnt) - 8388608.0f;
             return NORM ? quot_f32(c, dF, rinv) : c;
+        } else {
+            return NORM ? (float)((double)cnt / dD) : (float)cnt;
         }
-        return NORM ? (float)((double)cnt / dD) : (float)cnt;
     } else {
         return NORM ? (double)cnt / dD : (double)cnt;
     }
 }
 
+template <int OUT, int HIST_MODE, bool NORM, bool SMALL>
+__device__ __forceinline__ void seq_write_row(uint32_t *hist, typename OutT<OUT>::type *row, const SeqParams &p,
+                                              float dF, float rinv, double dD) {
+    using T = typename OutT<OUT>::type;
+    const uint32_t tid = threadIdx.x;
+    if ((p.dim & 3u) == 0) {
+        for (uint32_t j = tid * 4u; j < p.dim; j += blockDim.x * 4u) {
+            uint32_t cnt[4];
+            if constexpr (HIST_MODE == 1) {
+                const uint4 cc = __ldg(reinterpret_cast<const uint4 *>(p.canon_of_rank + j));
+                cnt[0] = hist[cc.x]; cnt[1] = hist[cc.y]; cnt[2] = hist[cc.z]; cnt[3] = hist[cc.w];
+                hist[cc.x] = 0; hist[cc.y] = 0; hist[cc.z] = 0; hist[cc.w] = 0;
+            } else {
+                const uint4 hv = *reinterpret_cast<const uint4 *>(hist + j);
+                cnt[0] = hv.x; cnt[1] = hv.y; cnt[2] = hv.z; cnt[3] = hv.w;
+                *reinterpret_cast<uint4 *>(hist + j) = make_uint4(0, 0, 0, 0);
+            }
+            const T e0 = cvt_count<OUT, NORM, SMALL>(cnt[0], dF, rinv, dD);
+            const T e1 = cvt_count<OUT, NORM, SMALL>(cnt[1], dF, rinv, dD);
+            const T e2 = cvt_count<OUT, NORM, SMALL>(cnt[2], dF, rinv, dD);
+            const T e3 = cvt_count<OUT, NORM, SMALL>(cnt[3], dF, rinv, dD);
+            if constexpr (OUT == OUT_F64) {
+                reinterpret_cast<double2 *>(row + j)[0] = make_double2(e0, e1);
+                reinterpret_cast<double2 *>(row + j)[1] = make_double2(e2, e3);
+            } else if constexpr (OUT == OUT_F32) {
+                *reinterpret_cast<float4 *>(row + j) = make_float4(e0, e1, e2, e3);
+            } else {
+                *reinterpret_cast<uint4 *>(row + j) = make_uint4(e0, e1, e2, e3);
+            }
+        }
+    } else {
+        for (uint32_t j = tid; j < p.dim; j += blockDim.x) {
+            uint32_t cnt;
+            if constexpr (HIST_MODE == 1) {
+                const uint32_t cc = __ldg(p.canon_of_rank + j);
+                cnt = hist[cc];
+                hist[cc] = 0;
+            } else {
+                cnt = hist[j];
+                hist[j] = 0;
+            }
+            row[j] = cvt_count<OUT, NORM, SMALL>(cnt, dF, rinv, dD);
+        }
+    }
+}
+
+// One CTA per sequence.  Warp w owns a contiguous range of the sequence's 16-base chunks and walks it
+// 32 chunks per step; the look-back word of lane 0 is carried from lane 31 of the previous step (the
+// first step is primed with the chunk before the range).  When every lane has 16 valid windows — the
+// steady state — the 16 atomics are unconditional increments; otherwise each adds its validity bit.
 template <int OUT, int HIST_MODE, bool NORM>
 __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
     extern __shared__ __align__(16) uint32_t hist[];
@@ -421,8 +476,8 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int nwarps = blockDim.x >> 5;
+    const uint32_t warp = tid >> 5;
+    const uint32_t nwarps = blockDim.x >> 5;
     const uint64_t nitems = p.list ? (uint64_t)*p.list_count : (p.n + p.group_size - 1) / p.group_size;
     if ((uint64_t)blockIdx.x >= nitems) return;  // nothing for this CTA (e.g. short_kernel took everything)
     for (uint32_t i = tid; i < p.hist_entries; i += blockDim.x) hist[i] = 0;
@@ -431,11 +486,12 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
     uint32_t it = 0;
 
     const uint32_t k = p.k;
-    const uint32_t kmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    const uint32_t kmask4 = ((k >= 15) ? 0x3FFFFFFFu : ((1u << (2 * k)) - 1u)) << 2;  // code pre-scaled by 4
     using T = typename OutT<OUT>::type;
     T *out = reinterpret_cast<T *>(p.out);
-    const bool vec_ok = (p.dim & 3u) == 0;
     constexpr uint32_t FULL = 0xffffffffu;
+    uint8_t *hbytes = reinterpret_cast<uint8_t *>(hist);
+    const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
 
     for (;;) {
         if (tid == 0) s_group = atomicAdd(p.counter, 1ULL);
@@ -453,61 +509,71 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
             const uint64_t s1 = p.offsets[seq + 1];
             uint32_t mine = 0;  // valid windows counted by this thread
             if (s1 - s0 >= k) {
-                // chunk c covers bases [16c, 16c+16); lane 0 of every warp re-reads the chunk before
-                // its warp's first emitting chunk as look-back, so a warp advances 31 chunks per step
-                const int64_t c_first = (int64_t)(s0 >> 4);
-                const int64_t c_last = (int64_t)((s1 - 1) >> 4);
-                const int64_t stride = (int64_t)nwarps * 31;
-                int64_t cb = c_first + (int64_t)warp * 31;
-                const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-                auto fetch = [&](int64_t cbase) -> uint4 {
-                    const int64_t c = cbase + lane - 1;
-                    if (c >= c_first && c <= c_last) return load16_guarded(p.bases, (uint64_t)c << 4, p.total_bases);
-                    return filler;
-                };
-                uint4 vnext = (cb <= c_last) ? fetch(cb) : filler;
-                for (; cb <= c_last; cb += stride) {
-                    const uint4 v = vnext;
-                    if (cb + stride <= c_last) vnext = fetch(cb + stride);  // prefetch the next strip
-                    const int64_t c = cb + lane - 1;
-                    uint32_t cf, vm;
-                    decode16(v, cf, vm);
-                    {   // keep only bases inside [s0, s1)
-                        const int64_t a = c << 4;
-                        const int64_t lo64 = (int64_t)s0 - a, hi64 = (int64_t)s1 - a;
-                        const uint32_t lo = lo64 > 0 ? (lo64 < 16 ? (uint32_t)lo64 : 16u) : 0u;
-                        const uint32_t hi = hi64 < 16 ? (hi64 > 0 ? (uint32_t)hi64 : 0u) : 16u;
-                        const uint32_t rm = (0xFFFFu >> lo) & ~(0xFFFFu >> hi);
-                        vm &= rm;
+                const uint64_t cbase = s0 >> 4;                                     // absolute index of chunk 0
+                const uint32_t nch = (uint32_t)(((s1 - 1) >> 4) - cbase) + 1u;      // chunks touching the sequence
+                // whole 32-chunk steps are dealt out to the warps in contiguous runs (only the last step
+                // of the sequence can be partial)
+                const uint32_t nsteps = (nch + 31) >> 5;
+                const uint32_t w0 = ((warp * nsteps) / nwarps) << 5;
+                const uint32_t w1 = min(nch, (((warp + 1) * nsteps) / nwarps) << 5);
+                const uint32_t head_mask = 0xFFFFu >> (uint32_t)(s0 & 15);          // bases of chunk 0 inside the sequence
+                const uint32_t tail_mask = ~(0xFFFFu >> ((uint32_t)((s1 - 1) & 15) + 1u)) & 0xFFFFu;
+                if (w0 < w1) {
+                    uint32_t carry_cf = 0, carry_vm = 0;
+                    if (w0 > 0) {  // prime the look-back with the chunk before this warp's range
+                        const uint4 v = load16_guarded(p.bases, (cbase + w0 - 1) << 4, p.total_bases);
+                        decode16(v, carry_cf, carry_vm);
+                        if (w0 == 1) carry_vm &= head_mask;
                     }
-                    const uint32_t cf_prev = __shfl_up_sync(FULL, cf, 1);
-                    const uint32_t vm_prev = __shfl_up_sync(FULL, vm, 1);
-                    // windows: bit b of vw set <=> V32 bits b..b+k-1 all set (older bases = higher bits)
-                    uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
-                    if (lane == 0) vw = 0;  // lane 0 only supplies look-back
-                    mine += __popc(vw);
-                    const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
-                    uint64_t R64 = 0;
-                    if constexpr (HIST_MODE == 1) {
-                        R64 = ((uint64_t)revcomp_pack(cf) << 32) | revcomp_pack(cf_prev);
-                    }
-                    uint32_t idx[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const uint32_t f = (uint32_t)(F64 >> (2 * (15 - j))) & kmask;
-                        if constexpr (HIST_MODE == 0) {
-                            idx[j] = f;
-                        } else if constexpr (HIST_MODE == 1) {
-                            const uint32_t r = (uint32_t)(R64 >> (2 * (17 + j - (int)k))) & kmask;
-                            idx[j] = min(f, r);
-                        } else {
-                            idx[j] = __ldg(p.rank_full + f);
+                    auto fetch = [&](uint32_t c) -> uint4 {
+                        return (c < w1) ? load16_guarded(p.bases, (cbase + c) << 4, p.total_bases) : filler;
+                    };
+                    uint4 vnext = fetch(w0 + lane);
+                    for (uint32_t c0 = w0; c0 < w1; c0 += 32) {
+                        const uint32_t c = c0 + lane;
+                        const uint4 v = vnext;
+                        if (c0 + 32 < w1) vnext = fetch(c + 32);  // prefetch the next step
+                        uint32_t cf, vm;
+                        decode16(v, cf, vm);
+                        if (c >= w1) { vm = 0; cf = (uint32_t)lane * 0x9E3779B1u; }  // idle lanes add 0 at scattered bins
+                        if (c == 0) vm &= head_mask;
+                        if (c == nch - 1) vm &= tail_mask;
+                        uint32_t cf_prev = __shfl_up_sync(FULL, cf, 1);
+                        uint32_t vm_prev = __shfl_up_sync(FULL, vm, 1);
+                        if (lane == 0) { cf_prev = carry_cf; vm_prev = carry_vm; }
+                        carry_cf = __shfl_sync(FULL, cf, 31);
+                        carry_vm = __shfl_sync(FULL, vm, 31);
+                        // windows: bit b of vw set <=> V32 bits b..b+k-1 all set (older bases = higher bits)
+                        const uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
+                        mine += __popc(vw);
+                        const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
+                        uint64_t R64 = 0;
+                        if constexpr (HIST_MODE == 1) {
+                            R64 = ((uint64_t)revcomp_pack(cf) << 32) | revcomp_pack(cf_prev);
                         }
-                    }
+                        uint32_t idx4[16];  // histogram byte offsets
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        // branch-free: an invalid window adds 0
-                        atomicAdd(&hist[idx[j]], (vw >> (15 - j)) & 1u);
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t f4 = (j < 15) ? ((uint32_t)(F64 >> (2 * (14 - j))) & kmask4)
+                                                         : ((cf << 2) & kmask4);
+                            if constexpr (HIST_MODE == 0) {
+                                idx4[j] = f4;
+                            } else if constexpr (HIST_MODE == 1) {
+                                const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
+                                idx4[j] = min(f4, r4);
+                            } else {
+                                idx4[j] = __ldg(p.rank_full + (f4 >> 2)) << 2;
+                            }
+                        }
+                        if (KTB_SEQ_FASTPATH && __all_sync(FULL, vw == 0xFFFFu)) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                atomicAdd(reinterpret_cast<uint32_t *>(hbytes + idx4[j]), 1u);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)  // branch-free: an invalid window adds 0
+                                atomicAdd(reinterpret_cast<uint32_t *>(hbytes + idx4[j]), (vw >> (15 - j)) & 1u);
+                        }
                     }
                 }
             }
@@ -520,52 +586,16 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
             if (tid == 0) s_total[(it + 1) & 1] = 0;  // slot of the next sequence; last read two barriers ago
             ++it;
             const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
-            const bool small_div = dv < (1ULL << 24);
             const float dF = (float)dv;
             const float rinv = __frcp_rn(dF);
             const double dD = (double)dv;
             if (tid == 0 && p.totals) p.totals[seq] = total;
             // ---- write-out (normalisation fused), histogram re-zeroed on the way
             T *row = out + seq * (uint64_t)p.dim;
-            if (vec_ok) {
-                for (uint32_t j = tid * 4u; j < p.dim; j += blockDim.x * 4u) {
-                    uint32_t cnt[4];
-                    if constexpr (HIST_MODE == 1) {
-                        const uint4 cc = __ldg(reinterpret_cast<const uint4 *>(p.canon_of_rank + j));
-                        cnt[0] = hist[cc.x]; cnt[1] = hist[cc.y]; cnt[2] = hist[cc.z]; cnt[3] = hist[cc.w];
-                        hist[cc.x] = 0; hist[cc.y] = 0; hist[cc.z] = 0; hist[cc.w] = 0;
-                    } else {
-                        const uint4 hv = *reinterpret_cast<const uint4 *>(hist + j);
-                        cnt[0] = hv.x; cnt[1] = hv.y; cnt[2] = hv.z; cnt[3] = hv.w;
-                        *reinterpret_cast<uint4 *>(hist + j) = make_uint4(0, 0, 0, 0);
-                    }
-                    T e0 = cvt_count<OUT, NORM>(cnt[0], small_div, dF, rinv, dD);
-                    T e1 = cvt_count<OUT, NORM>(cnt[1], small_div, dF, rinv, dD);
-                    T e2 = cvt_count<OUT, NORM>(cnt[2], small_div, dF, rinv, dD);
-                    T e3 = cvt_count<OUT, NORM>(cnt[3], small_div, dF, rinv, dD);
-                    if constexpr (OUT == OUT_F64) {
-                        reinterpret_cast<double2 *>(row + j)[0] = make_double2(e0, e1);
-                        reinterpret_cast<double2 *>(row + j)[1] = make_double2(e2, e3);
-                    } else if constexpr (OUT == OUT_F32) {
-                        *reinterpret_cast<float4 *>(row + j) = make_float4(e0, e1, e2, e3);
-                    } else {
-                        *reinterpret_cast<uint4 *>(row + j) = make_uint4(e0, e1, e2, e3);
-                    }
-                }
-            } else {
-                for (uint32_t j = tid; j < p.dim; j += blockDim.x) {
-                    uint32_t cnt;
-                    if constexpr (HIST_MODE == 1) {
-                        const uint32_t cc = __ldg(p.canon_of_rank + j);
-                        cnt = hist[cc];
-                        hist[cc] = 0;
-                    } else {
-                        cnt = hist[j];
-                        hist[j] = 0;
-                    }
-                    row[j] = cvt_count<OUT, NORM>(cnt, small_div, dF, rinv, dD);
-                }
-            }
+            if (dv < (1ULL << 23))
+                seq_write_row<OUT, HIST_MODE, NORM, true>(hist, row, p, dF, rinv, dD);
+            else
+                seq_write_row<OUT, HIST_MODE, NORM, false>(hist, row, p, dF, rinv, dD);
             __syncthreads();
         }
     }
