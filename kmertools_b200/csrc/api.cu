@@ -95,6 +95,7 @@ struct ktb_oligo {
     // device tables
     uint32_t *d_rank_full = nullptr;       // [4^k] any code -> rank of its canonical form
     uint32_t *d_canon_of_rank = nullptr;   // [dim_canon padded to 4]
+    uint32_t *d_canon_perm = nullptr;      // canon_of_rank permuted inside 128-rank blocks (seq_kernel gather)
     uint32_t *d_short_tab_canon = nullptr; // [4^k] (k <= 5): (word byte offset << 22) | 8*(bin&3)
     uint32_t *d_short_tab_raw = nullptr;
     unsigned long long *d_counters = nullptr;  // [4]
@@ -228,7 +229,7 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         SeqParams qp{};
         qp.bases = d_bases; qp.offsets = d_offsets; qp.n = n; qp.total_bases = total_bases;
         qp.out = d_out; qp.totals = d_totals;
-        qp.rank_full = h->d_rank_full; qp.canon_of_rank = h->d_canon_of_rank;
+        qp.rank_full = h->d_rank_full; qp.canon_of_rank = h->d_canon_of_rank; qp.canon_perm = h->d_canon_perm;
         qp.counter = h->d_counters + 1;
         qp.k = h->k; qp.dim = (uint32_t)dim; qp.hist_entries = (uint32_t)hist_entries;
         qp.norm_mode = norm_mode; qp.canonical = canonical;
@@ -383,6 +384,15 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
     while (cor.size() % 4) cor.push_back(0);
     CUB(cudaMalloc(&h->d_canon_of_rank, cor.size() * 4));
     CUB(cudaMemcpy(h->d_canon_of_rank, cor.data(), cor.size() * 4, cudaMemcpyHostToDevice));
+    {
+        std::vector<uint32_t> perm(cor.size(), 0);
+        const uint64_t nblk = h->dim_canon / 128;
+        for (uint64_t b = 0; b < nblk; ++b)
+            for (uint32_t l = 0; l < 32; ++l)
+                for (uint32_t e = 0; e < 4; ++e) perm[b * 128 + 4 * l + e] = cor[b * 128 + 32 * e + l];
+        CUB(cudaMalloc(&h->d_canon_perm, perm.size() * 4));
+        CUB(cudaMemcpy(h->d_canon_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
+    }
     if (h->ncodes <= (uint64_t)ktb::SHORT_MAX_CODES) {
         std::vector<uint32_t> tc(h->ncodes), tr(h->ncodes);
         for (uint64_t x = 0; x < h->ncodes; ++x) {
@@ -425,6 +435,7 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     h->ws_list.release();
     if (h->d_rank_full) cudaFree(h->d_rank_full);
     if (h->d_canon_of_rank) cudaFree(h->d_canon_of_rank);
+    if (h->d_canon_perm) cudaFree(h->d_canon_perm);
     if (h->d_short_tab_canon) cudaFree(h->d_short_tab_canon);
     if (h->d_short_tab_raw) cudaFree(h->d_short_tab_raw);
     if (h->d_counters) cudaFree(h->d_counters);
