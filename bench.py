@@ -174,15 +174,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads() -> int:
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the OS)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(spec: dict, bases_h: np.ndarray, offsets_h: np.ndarray, budget_reads: int):
     """Time the oracle's port of the reference path on a bounded prefix of the workload."""
     from oracle import oracle as O
     n = min(len(offsets_h) - 1, budget_reads)
     offs = np.ascontiguousarray(offsets_h[: n + 1]).astype(np.uint64)
     nb = int(offs[-1])
-    O.baseline_batch(bases_h[:nb], offs[: min(n, 1000) + 1], spec["k"], True, spec["norm"])  # warm
+    thr = host_threads()
+    O.baseline_batch(bases_h[:nb], offs[: min(n, 1000) + 1], spec["k"], True, spec["norm"], thr)  # warm
     t0 = time.perf_counter()
-    _, used = O.baseline_batch(bases_h[:nb], offs, spec["k"], True, spec["norm"])
+    _, used = O.baseline_batch(bases_h[:nb], offs, spec["k"], True, spec["norm"], thr)
     dt = time.perf_counter() - t0
     return nb / dt / 1e9, used, n, dt
 
@@ -195,17 +204,18 @@ def run_reference(args, spec, rank, world):
     L = spec["length"] if spec["length"] != "contigs" else 80_000
     # size the per-step sample for ~3 s of all-core CPU work
     from oracle import oracle as O
-    cores = O.max_threads()
-    reads = max(64, int(min(spec["n"] * args.scale, 3.0 * cores * 0.25e9 / L)))
+    cores = host_threads()
+    # ~3 s of all-core work per step at ~0.01 Gbases/s/core (measured: 0.15 Gbases/s on 16 cores)
+    reads = max(64, int(min(spec["n"] * args.scale, 3.0 * cores * 0.01e9 / L)))
     lengths = np.full(reads, L, dtype=np.uint64)
     offsets = np.zeros(reads + 1, dtype=np.uint64)
     np.cumsum(lengths, out=offsets[1:])
     bases = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(offsets[-1]), dtype=np.uint8)]
     for _ in range(args.warmup):
-        O.baseline_batch(bases, offsets, spec["k"], True, spec["norm"])
+        O.baseline_batch(bases, offsets, spec["k"], True, spec["norm"], cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, used = O.baseline_batch(bases, offsets, spec["k"], True, spec["norm"])
+        _, used = O.baseline_batch(bases, offsets, spec["k"], True, spec["norm"], cores)
     dt = (time.perf_counter() - t0) / args.steps
     val = int(offsets[-1]) / dt / 1e9
     sample = f"{reads} sequences x {L} bp per step ({int(offsets[-1])} bases)"
@@ -366,10 +376,9 @@ def main():
             bh, oh = keep_h[0].array, keep_h[1].array
         else:
             bh, oh = bases.cpu().numpy(), offsets.cpu().numpy().astype(np.uint64)
-        from oracle import oracle as O
-        cores = O.max_threads()
+        cores = host_threads()
         mean_len = max(1, total_bases // n)
-        budget = max(64, int(cores * 0.15e9 * 4 / mean_len))   # ~4 s at ~0.15 Gbases/s/core
+        budget = max(64, int(cores * 0.01e9 * 10 / mean_len))   # ~10 s at ~0.01 Gbases/s/core
         gb, used, ns, dt = cpu_sample(spec, bh, oh, budget)
         cpu = {"value": gb, "unit": "Gbases/s", "cores": used, "kind": "port",
                "sample": f"first {ns} sequences of the workload, {dt:.2f} s, C+OpenMP restatement of the reference "
