@@ -128,6 +128,43 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value);
 void *ktb_host_alloc(size_t bytes);
 void ktb_host_free(void *p);
 
+/* ---- file-level driver: `kmertools comp oligo` (kmertools/src/args.rs:70-103,242-263) ---------------
+ * Replaces OligoComputer::{new, set_*, vectorise} (composition/src/oligo.rs:31-229): reads FASTA/FASTQ
+ * (optionally .gz, "-" = stdin; ktio/src/seq.rs:29-155), computes the rows on the GPU and writes the
+ * same text the reference writes: header row (optional), one line per record, values "{:.6}" when
+ * normalising (formatted on the GPU) or integer counts, joined by `delim`.
+ * Format detection follows oligo.rs:88-105,173: stdin or counts mode sniff the first byte, otherwise
+ * the extension decides (unknown extension is an error; the reference panics there). */
+typedef struct ktb_file_opts {
+    const char *in_path;   /* "-" = stdin */
+    const char *out_path;
+    int k;                 /* args.rs restricts the CLI to 3..=7; the library accepts 1..KTB_MAX_K */
+    int canonical;         /* count_min = !raw_count */
+    int norm;              /* !counts */
+    char delim;            /* ' ', ',' or '\t' */
+    int header;
+    int threads;           /* accepted for CLI compatibility; host formatting threads for counts mode */
+    int device;            /* CUDA ordinal */
+} ktb_file_opts;
+
+typedef struct ktb_file_stats {
+    uint64_t records;
+    uint64_t bases;
+    uint64_t bytes_written;
+    double parse_ms, gpu_wait_ms, write_ms, total_ms;
+    uint64_t launches;
+} ktb_file_stats;
+
+int ktb_comp_oligo_file(const ktb_file_opts *opts, ktb_file_stats *stats /* optional */);
+
+/* Loads a whole FASTA/FASTQ(.gz) file into packed buffers (malloc'ed; release with ktb_free).
+ * sniff != 0: format from the first byte, else from the extension. */
+int ktb_fastx_load(const char *path, int sniff, uint8_t **bases, uint64_t **offsets, uint64_t *n);
+void ktb_free(void *p);
+
+/* Host build of the GPU text formatter: 8 characters "d.dddddd" = Rust's format!("{:.6}", q), q in [0,1]. */
+int ktb_debug_format6(double q, char *out8);
+
 /* Device byte -> 2-bit code table as the kernels compute it (256 entries); lets tests compare the
  * in-kernel decoder with SEQ_NT4_TABLE (kmer/src/kmer.rs:6-15). */
 int ktb_debug_nt4_table(ktb_oligo *h, uint8_t *out256);

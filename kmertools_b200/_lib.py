@@ -30,6 +30,18 @@ class Stats(C.Structure):
                 ("n_long", C.c_uint64), ("n_global", C.c_uint64)]
 
 
+class FileOpts(C.Structure):
+    _fields_ = [("in_path", C.c_char_p), ("out_path", C.c_char_p), ("k", C.c_int), ("canonical", C.c_int),
+                ("norm", C.c_int), ("delim", C.c_char), ("header", C.c_int), ("threads", C.c_int),
+                ("device", C.c_int)]
+
+
+class FileStats(C.Structure):
+    _fields_ = [("records", C.c_uint64), ("bases", C.c_uint64), ("bytes_written", C.c_uint64),
+                ("parse_ms", C.c_double), ("gpu_wait_ms", C.c_double), ("write_ms", C.c_double),
+                ("total_ms", C.c_double), ("launches", C.c_uint64)]
+
+
 # every symbol include/kmertools_b200.h declares: name -> (restype, argtypes)
 _VP, _U64, _I, _SZ = C.c_void_p, C.c_uint64, C.c_int, C.c_size_t
 SYMBOLS = {
@@ -46,6 +58,10 @@ SYMBOLS = {
     "ktb_oligo_set_option": (_I, [_VP, C.c_char_p, C.c_int64]),
     "ktb_host_alloc": (_VP, [_SZ]),
     "ktb_host_free": (None, [_VP]),
+    "ktb_comp_oligo_file": (_I, [C.POINTER(FileOpts), C.POINTER(FileStats)]),
+    "ktb_fastx_load": (_I, [C.c_char_p, _I, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_U64)]),
+    "ktb_free": (None, [_VP]),
+    "ktb_debug_format6": (_I, [C.c_double, C.c_char_p]),
     "ktb_debug_nt4_table": (_I, [_VP, _VP]),
     "ktb_last_error": (C.c_char_p, []),
     "ktb_abi_version": (_I, []),

@@ -14,6 +14,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIBDIR = HERE / "lib"
 LIB = LIBDIR / "libkmertools_b200.so"
+BIN = HERE / "bin" / "kmertools"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -40,7 +41,9 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*")) + [HERE.parent / "include" / "kmertools_b200.h", Path(__file__)]
+    deps = [d for d in CSRC.rglob("*") if d.is_file()] + [HERE.parent / "include" / "kmertools_b200.h", Path(__file__)]
+    if not BIN.exists():
+        return True
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -51,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     cmd = [nvcc(), *NVCC_FLAGS, *os.environ.get("KTB_NVCC_EXTRA", "").split()]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", str(LIB), *map(str, sources())]
+    cmd += ["-o", str(LIB), *map(str, sources()), "-lz"]
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
@@ -60,7 +63,22 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
+    build_cli(env)
     return LIB
+
+
+BIN = HERE / "bin" / "kmertools"
+
+
+def build_cli(env=None) -> Path:
+    """The `kmertools comp oligo` drop-in binary, linked against the shared library next to it."""
+    BIN.parent.mkdir(exist_ok=True)
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-o", str(BIN), str(CSRC / "cli" / "main.cpp"),
+           f"-L{LIBDIR}", "-lkmertools_b200", "-Wl,-rpath,$ORIGIN/../lib"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return BIN
 
 
 if __name__ == "__main__":

@@ -294,6 +294,24 @@ int dispatch_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offs
     }
 }
 
+}  // namespace
+
+// internal (hidden) entry points shared with file_api.cu
+__attribute__((visibility("hidden"))) int ktb_internal_dispatch(ktb_oligo *h, const uint8_t *d_bases,
+                                                               const uint64_t *d_offsets, uint64_t n,
+                                                               uint64_t total_bases, int canonical, int norm_mode,
+                                                               int out_dtype, void *d_out, uint64_t *d_totals,
+                                                               cudaStream_t st) {
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(KTB_ERR_CUDA, "cudaSetDevice failed");
+    return dispatch_device(h, d_bases, d_offsets, n, total_bases, canonical, norm_mode, out_dtype, d_out, d_totals, st);
+}
+__attribute__((visibility("hidden"))) int ktb_internal_fail(int code, const char *msg) { return fail(code, "%s", msg); }
+__attribute__((visibility("hidden"))) int ktb_internal_device(const ktb_oligo *h) { return h->device; }
+__attribute__((visibility("hidden"))) int ktb_internal_sms(const ktb_oligo *h) { return h->sm_count; }
+__attribute__((visibility("hidden"))) uint64_t ktb_internal_launches(const ktb_oligo *h) { return h->stats.launches; }
+
+namespace {
+
 int check_args(const ktb_oligo *h, int canonical, int norm_mode, int out_dtype) {
     if (!h) return fail(KTB_ERR_ARG, "null handle");
     if (canonical != 0 && canonical != 1) return fail(KTB_ERR_ARG, "canonical must be 0 or 1");
@@ -410,6 +428,9 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
         CUB(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         for (auto &e : s.ev) CUB(cudaEventCreate(&e));
     }
+    // cudaMemcpy from pageable memory may return while the DMA to the device is still in flight, and the
+    // handle's non-blocking streams do not order against the default stream: make the tables visible now.
+    CUB(cudaDeviceSynchronize());
 #undef CUB
     *out = h;
     return KTB_OK;

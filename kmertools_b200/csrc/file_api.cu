@@ -1,0 +1,291 @@
+// file_api.cu — file-level driver behind `kmertools comp oligo` (see include/kmertools_b200.h).
+// Host side: streaming FASTA/FASTQ parse into pinned, offset-indexed buffers; two buffer sets so that
+// parsing batch b+1 overlaps the GPU work and the D2H copy of batch b; sequential writes keep the
+// reference's row order.  Device side: counts (short/seq/flat kernels) + format_norm_kernel.
+#include "../../include/kmertools_b200.h"
+#include "fastx.h"
+#include "textfmt.cuh"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+int ktb_internal_dispatch(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n,
+                          uint64_t total_bases, int canonical, int norm_mode, int out_dtype, void *d_out,
+                          uint64_t *d_totals, cudaStream_t st);
+int ktb_internal_fail(int code, const char *msg);
+int ktb_internal_device(const ktb_oligo *h);
+int ktb_internal_sms(const ktb_oligo *h);
+uint64_t ktb_internal_launches(const ktb_oligo *h);
+
+namespace {
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct Pinned {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t bytes) {
+        if (bytes <= cap) return true;
+        void *q = nullptr;
+        if (cudaHostAlloc(&q, bytes, cudaHostAllocDefault) != cudaSuccess) return false;
+        if (p) cudaFreeHost(p);
+        p = q;
+        cap = bytes;
+        return true;
+    }
+    bool grow_keep(size_t bytes, size_t keep) {  // enlarge, preserving the first `keep` bytes
+        if (bytes <= cap) return true;
+        void *q = nullptr;
+        if (cudaHostAlloc(&q, bytes, cudaHostAllocDefault) != cudaSuccess) return false;
+        if (p && keep) memcpy(q, p, keep);
+        if (p) cudaFreeHost(p);
+        p = q;
+        cap = bytes;
+        return true;
+    }
+    ~Pinned() { if (p) cudaFreeHost(p); }
+};
+
+struct Dev {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t bytes) {
+        if (bytes <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (cudaMalloc(&p, bytes + bytes / 8 + 256) != cudaSuccess) { p = nullptr; return false; }
+        cap = bytes + bytes / 8 + 256;
+        return true;
+    }
+    ~Dev() { if (p) cudaFree(p); }
+};
+
+struct Set {
+    Pinned h_bases, h_offsets, h_out;
+    Dev d_bases, d_offsets, d_counts, d_totals, d_text;
+    cudaStream_t stream = nullptr;
+    uint64_t n = 0, nbases = 0, out_bytes = 0;
+    bool pending = false;
+    ~Set() { if (stream) cudaStreamDestroy(stream); }
+};
+
+// u32 counts -> "c0<d>c1<d>...\n" (format!("{}", f64) prints integral values without ".0", oligo.rs:138)
+size_t format_counts_rows(const uint32_t *counts, uint64_t n, uint32_t dim, char delim, std::vector<char> *out) {
+    out->resize((size_t)n * dim * 11 + 16);
+    char *o = out->data();
+    size_t w = 0;
+    for (uint64_t i = 0; i < n * (uint64_t)dim; ++i) {
+        uint32_t v = counts[i];
+        char tmp[10];
+        int len = 0;
+        do { tmp[len++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (len) o[w++] = tmp[--len];
+        o[w++] = ((i + 1) % dim == 0) ? '\n' : delim;
+    }
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ktb_debug_format6(double q, char *out8) {
+    if (!out8 || !(q >= 0.0 && q <= 1.0)) return ktb_internal_fail(KTB_ERR_ARG, "format6 needs q in [0,1]");
+    ktb::format6(q, out8);
+    return KTB_OK;
+}
+
+void ktb_free(void *p) { free(p); }
+
+int ktb_fastx_load(const char *path, int sniff, uint8_t **bases, uint64_t **offsets, uint64_t *n) {
+    if (!path || !bases || !offsets || !n) return ktb_internal_fail(KTB_ERR_ARG, "null argument");
+    *bases = nullptr; *offsets = nullptr; *n = 0;
+    ktb::ByteSource src;
+    std::string err;
+    if (!src.open(path, &err)) return ktb_internal_fail(KTB_ERR_IO, err.c_str());
+    ktb::SeqFormat fmt;
+    if (sniff) {
+        const int b = src.peek_first_byte();
+        fmt = (b == '>') ? ktb::SeqFormat::Fasta : ktb::SeqFormat::Fastq;
+        if (b < 0) { *offsets = (uint64_t *)calloc(1, 8); *bases = (uint8_t *)malloc(1); return KTB_OK; }
+    } else if (!ktb::format_from_path(path, &fmt)) {
+        return ktb_internal_fail(KTB_ERR_IO, "unknown sequence file extension (expected .fa/.fasta/.fna/.fq/.fastq[.gz])");
+    }
+    ktb::FastxParser parser(&src, fmt);
+    std::vector<uint8_t> buf(1 << 20);
+    std::vector<uint64_t> offs{0};
+    size_t used = 0;
+    for (;;) {
+        const long r = parser.fill(buf.data(), buf.size(), &used, &offs, (size_t)1 << 40);
+        if (r < 0) return ktb_internal_fail(KTB_ERR_IO, parser.error().c_str());
+        if (parser.eof()) break;
+        buf.resize(std::max(buf.size() * 2, used + parser.need_bytes() + 1024));
+    }
+    *n = offs.size() - 1;
+    *bases = (uint8_t *)malloc(used ? used : 1);
+    *offsets = (uint64_t *)malloc(offs.size() * 8);
+    if (!*bases || !*offsets) return ktb_internal_fail(KTB_ERR_NOMEM, "malloc failed");
+    if (used) memcpy(*bases, buf.data(), used);
+    memcpy(*offsets, offs.data(), offs.size() * 8);
+    return KTB_OK;
+}
+
+int ktb_comp_oligo_file(const ktb_file_opts *o, ktb_file_stats *stats) {
+    const double t_start = now_ms();
+    if (!o || !o->in_path || !o->out_path) return ktb_internal_fail(KTB_ERR_ARG, "null argument");
+    ktb_file_stats st{};
+    const bool norm = o->norm != 0;
+    const std::string in = o->in_path;
+
+    // ---- input + format (composition/src/oligo.rs:88-105,173)
+    ktb::ByteSource src;
+    std::string err;
+    if (!src.open(in, &err)) return ktb_internal_fail(KTB_ERR_IO, err.c_str());
+    ktb::SeqFormat fmt;
+    if (in == "-" || !norm) {
+        fmt = (src.peek_first_byte() == '>') ? ktb::SeqFormat::Fasta : ktb::SeqFormat::Fastq;
+    } else if (!ktb::format_from_path(in, &fmt)) {
+        return ktb_internal_fail(KTB_ERR_IO, "unknown sequence file extension (expected .fa/.fasta/.fna/.fq/.fastq[.gz])");
+    }
+    ktb::FastxParser parser(&src, fmt);
+
+    ktb_oligo *h = nullptr;
+    if (int rc = ktb_oligo_create(o->k, o->device, &h)) return rc;
+    struct Guard { ktb_oligo *h; ~Guard() { ktb_oligo_destroy(h); } } guard{h};
+    const uint64_t dim = ktb_oligo_dim(h, o->canonical);
+
+    FILE *fo = fopen(o->out_path, "wb");
+    if (!fo) return ktb_internal_fail(KTB_ERR_IO, (std::string("Unable to write to file: ") + o->out_path).c_str());
+    struct FGuard { FILE *f; ~FGuard() { if (f) fclose(f); } } fguard{fo};
+    std::vector<char> iobuf(8u << 20);
+    setvbuf(fo, iobuf.data(), _IOFBF, iobuf.size());
+
+    if (o->header) {  // get_header().join(delim) + "\n", oligo.rs:114-117
+        std::vector<char> hb(dim * o->k);
+        if (int rc = ktb_oligo_header(h, o->canonical, hb.data(), hb.size())) return rc;
+        std::string line;
+        line.reserve(dim * (o->k + 1));
+        for (uint64_t j = 0; j < dim; ++j) {
+            if (j) line.push_back(o->delim);
+            line.append(hb.data() + j * o->k, o->k);
+        }
+        line.push_back('\n');
+        fwrite(line.data(), 1, line.size(), fo);
+        st.bytes_written += line.size();
+    }
+
+    // ---- batch geometry
+    const size_t out_per_row = norm ? dim * 9 : dim * 4;
+    const size_t OUT_CAP = 256u << 20;
+    const size_t max_records = std::max<size_t>(1, std::min<size_t>(OUT_CAP / out_per_row, 4u << 20));
+    size_t bases_cap = 128u << 20;
+
+    Set sets[2];
+    for (auto &s : sets)
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess)
+            return ktb_internal_fail(KTB_ERR_CUDA, "cudaStreamCreate failed");
+    std::vector<char> text;
+    uint64_t launches = 0;
+
+    auto finish = [&](Set &s) -> int {  // wait for the batch, write its rows
+        if (!s.pending) return KTB_OK;
+        const double t0 = now_ms();
+        if (cudaStreamSynchronize(s.stream) != cudaSuccess)
+            return ktb_internal_fail(KTB_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+        const double t1 = now_ms();
+        st.gpu_wait_ms += t1 - t0;
+        size_t w;
+        if (norm) {
+            w = fwrite(s.h_out.p, 1, s.out_bytes, fo);
+            if (w != s.out_bytes) return ktb_internal_fail(KTB_ERR_IO, "short write");
+        } else {
+            const size_t len = format_counts_rows((const uint32_t *)s.h_out.p, s.n, (uint32_t)dim, o->delim, &text);
+            w = fwrite(text.data(), 1, len, fo);
+            if (w != len) return ktb_internal_fail(KTB_ERR_IO, "short write");
+        }
+        st.bytes_written += w;
+        st.write_ms += now_ms() - t1;
+        s.pending = false;
+        return KTB_OK;
+    };
+
+    std::vector<uint64_t> offs;
+    int b = 0;
+    for (;;) {
+        Set &s = sets[b & 1];
+        if (int rc = finish(s)) return rc;   // this set's previous batch (b-2) must be written first
+        const double tp0 = now_ms();
+        if (!s.h_bases.ensure(bases_cap)) return ktb_internal_fail(KTB_ERR_NOMEM, "pinned allocation failed");
+        offs.assign(1, 0);
+        size_t used = 0;
+        long got = 0;
+        for (;;) {
+            got = parser.fill((uint8_t *)s.h_bases.p, s.h_bases.cap, &used, &offs, max_records);
+            if (got < 0) return ktb_internal_fail(KTB_ERR_IO, parser.error().c_str());
+            if (got == 0 && parser.need_bytes() && used == 0) {  // one record larger than the buffer
+                bases_cap = parser.need_bytes() + (parser.need_bytes() >> 2) + 4096;
+                if (!s.h_bases.grow_keep(bases_cap, 0)) return ktb_internal_fail(KTB_ERR_NOMEM, "pinned allocation failed");
+                continue;
+            }
+            break;
+        }
+        st.parse_ms += now_ms() - tp0;
+        const uint64_t n = offs.size() - 1;
+        if (n == 0) break;
+        s.n = n;
+        s.nbases = used;
+        st.records += n;
+        st.bases += used;
+        // ---- enqueue H2D, kernels, D2H
+        if (!s.h_offsets.ensure((n + 1) * 8)) return ktb_internal_fail(KTB_ERR_NOMEM, "pinned allocation failed");
+        memcpy(s.h_offsets.p, offs.data(), (n + 1) * 8);
+        s.out_bytes = n * out_per_row;
+        if (!s.h_out.ensure(s.out_bytes) || !s.d_bases.ensure(used + 64) || !s.d_offsets.ensure((n + 1) * 8) ||
+            !s.d_counts.ensure(n * dim * 4) || !s.d_totals.ensure(n * 8) || (norm && !s.d_text.ensure(n * dim * 9)))
+            return ktb_internal_fail(KTB_ERR_NOMEM, "buffer allocation failed");
+        cudaMemcpyAsync(s.d_bases.p, s.h_bases.p, used, cudaMemcpyHostToDevice, s.stream);
+        cudaMemcpyAsync(s.d_offsets.p, s.h_offsets.p, (n + 1) * 8, cudaMemcpyHostToDevice, s.stream);
+        const uint64_t l0 = ktb_internal_launches(h);
+        (void)l0;
+        if (int rc = ktb_internal_dispatch(h, (const uint8_t *)s.d_bases.p, (const uint64_t *)s.d_offsets.p, n, used,
+                                           o->canonical, KTB_NORM_COUNTS, KTB_OUT_U32, s.d_counts.p,
+                                           (uint64_t *)s.d_totals.p, s.stream))
+            return rc;
+        launches += ktb_internal_launches(h);
+        if (norm) {
+            const uint64_t nel = n * dim;
+            uint64_t grid = (nel + 255) / 256;
+            const uint64_t cap = (uint64_t)ktb_internal_sms(h) * 16;
+            if (grid > cap) grid = cap;
+            ktb::format_norm_kernel<<<(unsigned)grid, 256, 0, s.stream>>>(
+                (const uint32_t *)s.d_counts.p, (const uint64_t *)s.d_totals.p, (uint8_t *)s.d_text.p, n, (uint32_t)dim,
+                o->delim, KTB_NORM_CLI, o->canonical);
+            ++launches;
+            cudaMemcpyAsync(s.h_out.p, s.d_text.p, s.out_bytes, cudaMemcpyDeviceToHost, s.stream);
+        } else {
+            cudaMemcpyAsync(s.h_out.p, s.d_counts.p, s.out_bytes, cudaMemcpyDeviceToHost, s.stream);
+        }
+        if (cudaGetLastError() != cudaSuccess) return ktb_internal_fail(KTB_ERR_CUDA, "enqueue failed");
+        s.pending = true;
+        ++b;
+        if (parser.eof()) break;
+    }
+    // drain in order: the older batch first
+    if (int rc = finish(sets[b & 1])) return rc;
+    if (int rc = finish(sets[(b + 1) & 1])) return rc;
+    if (fflush(fo) != 0) return ktb_internal_fail(KTB_ERR_IO, "flush failed");
+    st.launches = launches;
+    st.total_ms = now_ms() - t_start;
+    if (stats) *stats = st;
+    return KTB_OK;
+}
+
+}  // extern "C"

@@ -27,7 +27,10 @@
 static uint8_t NT4[256];
 static int nt4_ready = 0;
 
-static void nt4_init(void) {
+/* Runs at load time (constructor) so the table is complete before any OpenMP region can race on it:
+ * a lazy first-use init inside the parallel batch driver let one thread re-memset the table while
+ * another was decoding with it (found in round 1: first oracle call of a process under-counted). */
+__attribute__((constructor)) static void nt4_init(void) {
     if (nt4_ready) return;
     memset(NT4, 4, sizeof NT4);
     NT4[0] = 0; NT4[1] = 1; NT4[2] = 2; NT4[3] = 3;
