@@ -244,6 +244,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--short-variant", type=int, default=None)
     ap.add_argument("--force-path", type=int, default=None)
+    ap.add_argument("--seq-threads", type=int, default=None)
+    ap.add_argument("--global-wave-mb", type=int, default=None)
     args = ap.parse_args()
     spec = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -273,6 +275,10 @@ def main():
         oc.set_option("short_variant", args.short_variant)
     if args.force_path is not None:
         oc.set_option("force_path", args.force_path)
+    if args.seq_threads is not None:
+        oc.set_option("seq_threads", args.seq_threads)
+    if args.global_wave_mb is not None:
+        oc.set_option("global_wave_bytes", args.global_wave_mb << 20)
     bases, offsets = make_workload(spec, args.scale, dev)
     n = offsets.numel() - 1
     total_bases = int(offsets[-1])

@@ -101,6 +101,8 @@ struct ktb_oligo {
     unsigned long long *d_counters = nullptr;  // [4]
     DevBuf ws_totals, ws_counts, ws_list;
     ChunkSet sets[NBUF];
+    cudaStream_t aux[2] = {nullptr, nullptr};   // wave overlap in the global-atomic path
+    cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
     int sm_count = 0;
     size_t smem_optin = 0;
     // options
@@ -108,6 +110,8 @@ struct ktb_oligo {
     int force_path = 0;
     int short_variant = 0;
     int short_warps = 0;  // 0 = auto
+    int seq_threads = 0;  // 0 = auto (256)
+    int64_t global_wave_bytes = 64ll << 20;  // rows zeroed + counted together in the global-atomic path (fits L2)
     ktb_stats stats{};
 };
 
@@ -172,13 +176,14 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     else kern = nrm ? seq_kernel<OUT, 2, true> : seq_kernel<OUT, 2, false>;
     if (int rc = set_smem(kern, smem)) return rc;
     int per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    const int threads = h->seq_threads > 0 ? h->seq_threads : 256;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)h->sm_count * per_sm;
     const uint64_t ngroups = (p.n + p.group_size - 1) / p.group_size;
     if (grid > ngroups) grid = ngroups;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, 256, smem, st>>>(p);
+    kern<<<(unsigned)grid, threads, smem, st>>>(p);
     CU(cudaGetLastError());
     h->stats.launches++;
     return KTB_OK;
@@ -239,44 +244,102 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         return launch_seq<OUT>(h, qp, hist_mode, st);
     }
 
-    // ---- global-atomic path: zeroed u32 rows, flat decomposition, finalize
-    uint32_t *counts = nullptr;
-    if (OUT == OUT_F64) {
-        if (int rc = h->ws_counts.ensure(n * dim * 4)) return rc;
-        counts = (uint32_t *)h->ws_counts.p;
-    } else {
-        counts = (uint32_t *)d_out;
-    }
+    // ---- global-atomic path: zeroed u32 rows in HBM/L2, RED atomics, finalize
     if (int rc = h->ws_totals.ensure(n * 8)) return rc;
     unsigned long long *tot = (unsigned long long *)h->ws_totals.p;
-    CU(cudaMemsetAsync(counts, 0, n * dim * 4, st));
     CU(cudaMemsetAsync(tot, 0, n * 8, st));
-    if (total_bases > 0) {
-        FlatParams fp{};
-        fp.bases = d_bases; fp.offsets = d_offsets; fp.n = n; fp.total_bases = total_bases;
-        fp.counts = counts; fp.totals = tot;
-        fp.rank_full = canonical ? h->d_rank_full : nullptr;
-        fp.dim = dim; fp.k = h->k;
-        const uint64_t nchunks = (total_bases + FLAT_CHUNK - 1) / FLAT_CHUNK;
-        uint64_t grid = (nchunks + 255) / 256;
-        const uint64_t cap = (uint64_t)h->sm_count * 32;
-        if (grid > cap) grid = cap;
-        flat_kernel<<<(unsigned)grid, 256, 0, st>>>(fp);
-        CU(cudaGetLastError());
-        h->stats.launches++;
-    }
-    if (OUT == OUT_U32) {
-        if (d_totals) CU(cudaMemcpyAsync(d_totals, tot, n * 8, cudaMemcpyDeviceToDevice, st));
-    } else {
-        uint64_t nel = n * dim;
+    const uint64_t row_bytes = dim * 4;
+    auto finalize = [&](const uint32_t *counts, uint64_t i0, uint64_t cnt) -> int {
+        if (OUT == OUT_U32) return KTB_OK;   // counts are already the output
+        const uint64_t nel = cnt * dim;
         uint64_t grid = (nel + 255) / 256;
         const uint64_t cap = (uint64_t)h->sm_count * 16;
         if (grid > cap) grid = cap;
-        finalize_kernel<OUT><<<(unsigned)grid, 256, 0, st>>>(counts, tot, d_out, d_totals, n, dim,
-                                                            norm_mode, canonical);
+        finalize_kernel<OUT><<<(unsigned)grid, 256, 0, st>>>(counts, tot + i0, (uint8_t *)d_out + i0 * dim * esize,
+                                                            nullptr, cnt, dim, norm_mode, canonical);
         CU(cudaGetLastError());
         h->stats.launches++;
+        return KTB_OK;
+    };
+    if (h->force_path == 1) {   // testing: the flat-decomposition fallback, whole batch at once
+        uint32_t *counts = (uint32_t *)d_out;
+        if (OUT == OUT_F64) {
+            if (int rc = h->ws_counts.ensure(n * row_bytes)) return rc;
+            counts = (uint32_t *)h->ws_counts.p;
+        }
+        CU(cudaMemsetAsync(counts, 0, n * row_bytes, st));
+        if (total_bases > 0) {
+            FlatParams fp{};
+            fp.bases = d_bases; fp.offsets = d_offsets; fp.n = n; fp.total_bases = total_bases;
+            fp.counts = counts; fp.totals = tot;
+            fp.rank_full = canonical ? h->d_rank_full : nullptr;
+            fp.dim = dim; fp.k = h->k;
+            const uint64_t nchunks = (total_bases + FLAT_CHUNK - 1) / FLAT_CHUNK;
+            uint64_t grid = (nchunks + 255) / 256;
+            const uint64_t cap = (uint64_t)h->sm_count * 32;
+            if (grid > cap) grid = cap;
+            flat_kernel<<<(unsigned)grid, 256, 0, st>>>(fp);
+            CU(cudaGetLastError());
+            h->stats.launches++;
+        }
+        if (int rc = finalize(counts, 0, n)) return rc;
+    } else {
+        // Waves of rows that fit L2 together: zero the wave's rows, let every CTA of the GPU work on that
+        // wave (sequences are split into tiles), normalise it, move on.  The REDs then hit rows that are
+        // still L2-resident and each row goes to HBM once; one big memset + one launch over the whole
+        // batch made every RED a 32-byte DRAM read-modify-write (measured 8.5 ms vs the 0.7 ms roofline).
+        SeqParams qp{};
+        qp.bases = d_bases; qp.offsets = d_offsets; qp.n = n; qp.total_bases = total_bases;
+        qp.rank_full = canonical ? h->d_rank_full : nullptr;
+        qp.counter = h->d_counters + 1;
+        qp.k = h->k; qp.dim = (uint32_t)dim; qp.hist_entries = 0;
+        qp.norm_mode = norm_mode; qp.canonical = canonical;
+        qp.list = nullptr; qp.list_count = nullptr; qp.group_size = 1;
+        qp.gtotals = tot;
+        auto kern = seq_kernel<OUT_U32, 3, false>;
+        const int threads = h->seq_threads > 0 ? h->seq_threads : 128;
+        int per_sm = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
+        const uint64_t ctas = (uint64_t)h->sm_count * std::max(per_sm, 1);
+        // two waves in flight (one per helper stream), each half of the L2 budget
+        const uint64_t wave = std::max<uint64_t>(1, std::min<uint64_t>(n, (uint64_t)h->global_wave_bytes / 2 / row_bytes));
+        if (OUT == OUT_F64)
+            if (int rc = h->ws_counts.ensure(2 * wave * row_bytes)) return rc;
+        // a work item = (sequence, tile); aim at ~4 steps of 512 bases per warp
+        const uint64_t mean_steps = (total_bases / std::max<uint64_t>(n, 1)) / 512 + 1;
+        const uint32_t tiles = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(256, mean_steps / (4 * (threads / 32))));
+        CU(cudaEventRecord(h->aux_ev[2], st));
+        uint64_t w = 0;
+        for (uint64_t i0 = 0; i0 < n; i0 += wave, ++w) {
+            const int x = (int)(w & 1);
+            cudaStream_t sx = h->aux[x];
+            if (w < 2) CU(cudaStreamWaitEvent(sx, h->aux_ev[2], 0));
+            const uint64_t cnt = std::min(wave, n - i0);
+            uint32_t *counts = (OUT == OUT_F64) ? (uint32_t *)h->ws_counts.p + (uint64_t)x * wave * dim
+                                                : (uint32_t *)d_out + i0 * dim;
+            CU(cudaMemsetAsync(counts, 0, cnt * row_bytes, sx));
+            CU(cudaMemsetAsync(h->d_counters + 4 + x, 0, sizeof(unsigned long long), sx));
+            qp.counter = h->d_counters + 4 + x;
+            qp.gcounts = counts; qp.seq_base = i0; qp.seq_count = cnt; qp.tiles = tiles;
+            const uint64_t items = cnt * tiles;
+            kern<<<(unsigned)std::min(ctas, items), threads, 0, sx>>>(qp);
+            CU(cudaGetLastError());
+            h->stats.launches++;
+            if (OUT != OUT_U32) {
+                const uint64_t nel = cnt * dim;
+                uint64_t grid = std::min<uint64_t>((nel + 255) / 256, (uint64_t)h->sm_count * 16);
+                finalize_kernel<OUT><<<(unsigned)grid, 256, 0, sx>>>(counts, tot + i0, (uint8_t *)d_out + i0 * dim * esize,
+                                                                    nullptr, cnt, dim, norm_mode, canonical);
+                CU(cudaGetLastError());
+                h->stats.launches++;
+            }
+        }
+        for (int x = 0; x < 2; ++x) {   // join the helper streams back into the caller's stream
+            CU(cudaEventRecord(h->aux_ev[x], h->aux[x]));
+            CU(cudaStreamWaitEvent(st, h->aux_ev[x], 0));
+        }
     }
+    if (d_totals) CU(cudaMemcpyAsync(d_totals, tot, n * 8, cudaMemcpyDeviceToDevice, st));
     (void)esize;
     return KTB_OK;
 }
@@ -423,11 +486,13 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
         CUB(cudaMemcpy(h->d_short_tab_canon, tc.data(), h->ncodes * 4, cudaMemcpyHostToDevice));
         CUB(cudaMemcpy(h->d_short_tab_raw, tr.data(), h->ncodes * 4, cudaMemcpyHostToDevice));
     }
-    CUB(cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)));
+    CUB(cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)));
     for (auto &s : h->sets) {
         CUB(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         for (auto &e : s.ev) CUB(cudaEventCreate(&e));
     }
+    for (auto &a : h->aux) CUB(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    for (auto &e : h->aux_ev) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     // cudaMemcpy from pageable memory may return while the DMA to the device is still in flight, and the
     // handle's non-blocking streams do not order against the default stream: make the tables visible now.
     CUB(cudaDeviceSynchronize());
@@ -451,6 +516,8 @@ void ktb_oligo_destroy(ktb_oligo *h) {
         s.out.release();
         s.totals.release();
     }
+    for (auto &a : h->aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+    for (auto &e : h->aux_ev) if (e) cudaEventDestroy(e);
     h->ws_totals.release();
     h->ws_counts.release();
     h->ws_list.release();
@@ -507,6 +574,12 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->short_variant = (int)value;
     } else if (!strcmp(key, "short_warps")) {
         h->short_warps = (int)value;
+    } else if (!strcmp(key, "global_wave_bytes")) {
+        if (value < 1) return fail(KTB_ERR_ARG, "global_wave_bytes must be positive");
+        h->global_wave_bytes = value;
+    } else if (!strcmp(key, "seq_threads")) {
+        if (value != 0 && (value < 32 || value > KTB_SEQ_MAXTHREADS || value % 32)) return fail(KTB_ERR_ARG, "seq_threads must be a multiple of 32 in 32..%d", KTB_SEQ_MAXTHREADS);
+        h->seq_threads = (int)value;
     } else {
         return fail(KTB_ERR_ARG, "unknown option '%s'", key);
     }

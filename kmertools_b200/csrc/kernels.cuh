@@ -21,6 +21,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef KTB_SEQ_MAXTHREADS
+#define KTB_SEQ_MAXTHREADS 256
+#endif
+#ifndef KTB_SEQ_MINBLOCKS
+#define KTB_SEQ_MINBLOCKS 3
+#endif
 #ifndef KTB_SEQ_FASTPATH
 #define KTB_SEQ_FASTPATH 0
 #endif
@@ -397,8 +403,15 @@ struct SeqParams {
     const uint32_t *list;        // groups to process (short_kernel's rejects); nullptr = every group
     const unsigned long long *list_count;
     uint32_t group_size;         // sequences per group (SHORT_G)
+    uint32_t *gcounts;           // HIST_MODE 3: zeroed u32 rows of this wave (row 0 = sequence seq_base)
+    unsigned long long *gtotals; // HIST_MODE 3: per-sequence window totals, zeroed (finalize_kernel reads them)
+    uint64_t seq_base;           // HIST_MODE 3: first sequence of this wave
+    uint64_t seq_count;          // HIST_MODE 3: sequences in this wave
+    uint32_t tiles;              // HIST_MODE 3: CTAs cooperating on one sequence (work item = sequence x tile)
 };
 
+// HIST_MODE 3 = histogram too large for shared memory: atomics (RED) go straight to the zeroed u32 row in
+//             global memory / L2, index rank_full[f] (or f when rank_full is null); no write-out here.
 // HIST_MODE: 0 = raw (index f), 1 = canonical code space (index min(f,r), gather on write-out),
 //            2 = canonical rank space (index rank_full[f], linear write-out)
 // count -> output element.  SMALL: every count (and the divisor) is below 2^23, so the float comes
@@ -496,7 +509,7 @@ __device__ __forceinline__ void seq_write_row(uint32_t *hist, typename OutT<OUT>
 // first step is primed with the chunk before the range).  When every lane has 16 valid windows — the
 // steady state — the 16 atomics are unconditional increments; otherwise each adds its validity bit.
 template <int OUT, int HIST_MODE, bool NORM>
-__global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
+__global__ void __launch_bounds__(KTB_SEQ_MAXTHREADS, KTB_SEQ_MINBLOCKS) seq_kernel(const SeqParams p) {
     extern __shared__ __align__(16) uint32_t hist[];
     __shared__ unsigned long long s_group;
     __shared__ uint32_t s_total[2];  // double-buffered so the reset never races a late reader
@@ -505,7 +518,8 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
     const int lane = tid & 31;
     const uint32_t warp = tid >> 5;
     const uint32_t nwarps = blockDim.x >> 5;
-    const uint64_t nitems = p.list ? (uint64_t)*p.list_count : (p.n + p.group_size - 1) / p.group_size;
+    const uint64_t nitems = (HIST_MODE == 3) ? p.seq_count * p.tiles
+                            : (p.list ? (uint64_t)*p.list_count : (p.n + p.group_size - 1) / p.group_size);
     if ((uint64_t)blockIdx.x >= nitems) return;  // nothing for this CTA (e.g. short_kernel took everything)
     for (uint32_t i = tid; i < p.hist_entries; i += blockDim.x) hist[i] = 0;
     if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
@@ -526,9 +540,18 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
         const unsigned long long item = s_group;
         __syncthreads();  // everyone has read s_group before tid 0 overwrites it next round
         if (item >= nitems) break;
-        const uint64_t g = p.list ? (uint64_t)p.list[item] : (uint64_t)item;
-        const uint64_t i0 = g * (uint64_t)p.group_size;
-        const uint32_t nseq = (uint32_t)min((unsigned long long)p.group_size, (unsigned long long)(p.n - i0));
+        uint64_t i0;
+        uint32_t nseq, tile = 0, tiles = 1;
+        if constexpr (HIST_MODE == 3) {  // work item = (sequence of the wave, tile of that sequence)
+            tiles = p.tiles;
+            i0 = p.seq_base + item / tiles;
+            tile = (uint32_t)(item % tiles);
+            nseq = 1;
+        } else {
+            const uint64_t g = p.list ? (uint64_t)p.list[item] : (uint64_t)item;
+            i0 = g * (uint64_t)p.group_size;
+            nseq = (uint32_t)min((unsigned long long)p.group_size, (unsigned long long)(p.n - i0));
+        }
 
         for (uint32_t si = 0; si < nseq; ++si) {
             const uint64_t seq = i0 + si;
@@ -541,8 +564,10 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
                 // whole 32-chunk steps are dealt out to the warps in contiguous runs (only the last step
                 // of the sequence can be partial)
                 const uint32_t nsteps = (nch + 31) >> 5;
-                const uint32_t w0 = ((warp * nsteps) / nwarps) << 5;
-                const uint32_t w1 = min(nch, (((warp + 1) * nsteps) / nwarps) << 5);
+                const uint32_t ts0 = (uint32_t)(((uint64_t)tile * nsteps) / tiles);        // this CTA's steps
+                const uint32_t ts1 = (uint32_t)(((uint64_t)(tile + 1) * nsteps) / tiles);
+                const uint32_t w0 = (ts0 + (warp * (ts1 - ts0)) / nwarps) << 5;
+                const uint32_t w1 = min(nch, (ts0 + ((warp + 1) * (ts1 - ts0)) / nwarps) << 5);
                 const uint32_t head_mask = 0xFFFFu >> (uint32_t)(s0 & 15);          // bases of chunk 0 inside the sequence
                 const uint32_t tail_mask = ~(0xFFFFu >> ((uint32_t)((s1 - 1) & 15) + 1u)) & 0xFFFFu;
                 if (w0 < w1) {
@@ -588,9 +613,18 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
                             } else if constexpr (HIST_MODE == 1) {
                                 const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
                                 idx4[j] = min(f4, r4);
-                            } else {
+                            } else if constexpr (HIST_MODE == 2) {
                                 idx4[j] = __ldg(p.rank_full + (f4 >> 2)) << 2;
+                            } else {
+                                idx4[j] = p.rank_full ? (__ldg(p.rank_full + (f4 >> 2)) << 2) : f4;
                             }
+                        }
+                        if constexpr (HIST_MODE == 3) {
+                            uint8_t *grow = reinterpret_cast<uint8_t *>(p.gcounts + (seq - p.seq_base) * (uint64_t)p.dim);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (vw & (1u << (15 - j))) atomicAdd(reinterpret_cast<uint32_t *>(grow + idx4[j]), 1u);
+                            continue;
                         }
                         if (KTB_SEQ_FASTPATH && __all_sync(FULL, vw == 0xFFFFu)) {
 #pragma unroll
@@ -616,6 +650,11 @@ __global__ void __launch_bounds__(256) seq_kernel(const SeqParams p) {
             const float dF = (float)dv;
             const float rinv = __frcp_rn(dF);
             const double dD = (double)dv;
+            if constexpr (HIST_MODE == 3) {
+                if (tid == 0 && total) atomicAdd(p.gtotals + seq, (unsigned long long)total);
+                __syncthreads();
+                continue;
+            }
             if (tid == 0 && p.totals) p.totals[seq] = total;
             // ---- write-out (normalisation fused), histogram re-zeroed on the way
             T *row = out + seq * (uint64_t)p.dim;
