@@ -174,6 +174,17 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     if (hist_mode == 0) kern = nrm ? seq_kernel<OUT, 0, true> : seq_kernel<OUT, 0, false>;
     else if (hist_mode == 1) kern = nrm ? seq_kernel<OUT, 1, true> : seq_kernel<OUT, 1, false>;
     else kern = nrm ? seq_kernel<OUT, 2, true> : seq_kernel<OUT, 2, false>;
+    if constexpr (OUT == OUT_F32) {   // k folded into immediates for the headline shapes
+        if (hist_mode == 1 && nrm) {
+            switch (p.k) {
+                case 4: kern = seq_kernel<OUT_F32, 1, true, 4>; break;
+                case 5: kern = seq_kernel<OUT_F32, 1, true, 5>; break;
+                case 6: kern = seq_kernel<OUT_F32, 1, true, 6>; break;
+                case 7: kern = seq_kernel<OUT_F32, 1, true, 7>; break;
+                default: break;
+            }
+        }
+    }
     if (int rc = set_smem(kern, smem)) return rc;
     int per_sm = 1;
     const int threads = h->seq_threads > 0 ? h->seq_threads : 256;

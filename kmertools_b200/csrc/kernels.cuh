@@ -28,7 +28,7 @@
 #define KTB_SEQ_MINBLOCKS 3
 #endif
 #ifndef KTB_SEQ_FASTPATH
-#define KTB_SEQ_FASTPATH 0
+#define KTB_SEQ_FASTPATH 1
 #endif
 
 namespace ktb {
@@ -508,7 +508,9 @@ __device__ __forceinline__ void seq_write_row(uint32_t *hist, typename OutT<OUT>
 // 32 chunks per step; the look-back word of lane 0 is carried from lane 31 of the previous step (the
 // first step is primed with the chunk before the range).  When every lane has 16 valid windows — the
 // steady state — the 16 atomics are unconditional increments; otherwise each adds its validity bit.
-template <int OUT, int HIST_MODE, bool NORM>
+// KT: compile-time k (0 = use p.k); the specialised instances fold the window-mask loop and every
+// shift amount into immediates.
+template <int OUT, int HIST_MODE, bool NORM, int KT = 0>
 __global__ void __launch_bounds__(KTB_SEQ_MAXTHREADS, KTB_SEQ_MINBLOCKS) seq_kernel(const SeqParams p) {
     extern __shared__ __align__(16) uint32_t hist[];
     __shared__ unsigned long long s_group;
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(KTB_SEQ_MAXTHREADS, KTB_SEQ_MINBLOCKS) seq_ker
     __syncthreads();
     uint32_t it = 0;
 
-    const uint32_t k = p.k;
+    const uint32_t k = KT ? (uint32_t)KT : p.k;
     const uint32_t kmask4 = ((k >= 15) ? 0x3FFFFFFFu : ((1u << (2 * k)) - 1u)) << 2;  // code pre-scaled by 4
     using T = typename OutT<OUT>::type;
     T *out = reinterpret_cast<T *>(p.out);
