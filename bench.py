@@ -384,7 +384,7 @@ def main():
             bh, oh = bases.cpu().numpy(), offsets.cpu().numpy().astype(np.uint64)
         cores = host_threads()
         mean_len = max(1, total_bases // n)
-        budget = max(64, int(cores * 0.01e9 * 10 / mean_len))   # ~10 s at ~0.01 Gbases/s/core
+        budget = max(64, int(cores * 0.01e9 * 3 / mean_len))   # same bounded sample as --impl reference (~3 s)
         gb, used, ns, dt = cpu_sample(spec, bh, oh, budget)
         cpu = {"value": gb, "unit": "Gbases/s", "cores": used, "kind": "port",
                "sample": f"first {ns} sequences of the workload, {dt:.2f} s, C+OpenMP restatement of the reference "
