@@ -36,6 +36,10 @@ WORKLOADS = {
                         desc="10M x 150bp short reads, k=5 canonical f32 normalised (BASELINE configs[1])"),
     "reads10k_k7": dict(n=1_000_000, length=10_000, k=7, dtype="f32", norm=1, seed=20250002,
                         desc="1M x 10kbp long reads, k=7 canonical f32 normalised (BASELINE configs[2])"),
+    "reads10k_k6": dict(n=1_000_000, length=10_000, k=6, dtype="f32", norm=1, seed=20250002,
+                        desc="1M x 10kbp long reads, k=6 canonical f32 normalised (occupancy probe, not a BASELINE config)"),
+    "reads10k_k5": dict(n=1_000_000, length=10_000, k=5, dtype="f32", norm=1, seed=20250002,
+                        desc="1M x 10kbp long reads, k=5 canonical f32 normalised (occupancy probe, not a BASELINE config)"),
     "contigs_k4": dict(n=20_000, length="contigs", k=4, dtype="f32", norm=1, seed=20250003,
                        desc="20k metagenome contigs 1-500kbp with N runs, k=4 (BASELINE configs[3])"),
     "reads10k_k8": dict(n=100_000, length=10_000, k=8, dtype="u32", norm=0, seed=20250004,
@@ -246,6 +250,7 @@ def main():
     ap.add_argument("--force-path", type=int, default=None)
     ap.add_argument("--seq-threads", type=int, default=None)
     ap.add_argument("--global-wave-mb", type=int, default=None)
+    ap.add_argument("--dense-odd", type=int, default=None)
     args = ap.parse_args()
     spec = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -277,6 +282,8 @@ def main():
         oc.set_option("force_path", args.force_path)
     if args.seq_threads is not None:
         oc.set_option("seq_threads", args.seq_threads)
+    if args.dense_odd is not None:
+        oc.set_option("dense_odd", args.dense_odd)
     if args.global_wave_mb is not None:
         oc.set_option("global_wave_bytes", args.global_wave_mb << 20)
     bases, offsets = make_workload(spec, args.scale, dev)

@@ -96,6 +96,8 @@ struct ktb_oligo {
     uint32_t *d_rank_full = nullptr;       // [4^k] any code -> rank of its canonical form
     uint32_t *d_canon_of_rank = nullptr;   // [dim_canon padded to 4]
     uint32_t *d_canon_perm = nullptr;      // canon_of_rank permuted inside 128-rank blocks (seq_kernel gather)
+    uint32_t *d_mb_of_rank = nullptr;      // odd k: rank -> dense middle-base index (seq_kernel mode 4)
+    uint32_t *d_mb_perm = nullptr;
     uint32_t *d_short_tab_canon = nullptr; // [4^k] (k <= 5): (word byte offset << 22) | 8*(bin&3)
     uint32_t *d_short_tab_raw = nullptr;
     unsigned long long *d_counters = nullptr;  // [4]
@@ -111,6 +113,7 @@ struct ktb_oligo {
     int short_variant = 0;
     int short_warps = 0;  // 0 = auto
     int seq_threads = 0;  // 0 = auto (256)
+    int dense_odd = 1;    // use seq_kernel mode 4 where it applies
     int64_t global_wave_bytes = 64ll << 20;  // rows zeroed + counted together in the global-atomic path (fits L2)
     ktb_stats stats{};
 };
@@ -173,8 +176,10 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     const bool nrm = p.norm_mode != NORM_COUNTS;
     if (hist_mode == 0) kern = nrm ? seq_kernel<OUT, 0, true> : seq_kernel<OUT, 0, false>;
     else if (hist_mode == 1) kern = nrm ? seq_kernel<OUT, 1, true> : seq_kernel<OUT, 1, false>;
+    else if (hist_mode == 4) kern = nrm ? seq_kernel<OUT, 4, true> : seq_kernel<OUT, 4, false>;
     else kern = nrm ? seq_kernel<OUT, 2, true> : seq_kernel<OUT, 2, false>;
-    if constexpr (OUT == OUT_F32) {   // k folded into immediates for the headline shapes
+    if constexpr (OUT == OUT_F32) {
+        if (hist_mode == 4 && nrm && p.k == 7) kern = seq_kernel<OUT_F32, 4, true, 7>;   // k folded into immediates for the headline shapes
         if (hist_mode == 1 && nrm) {
             switch (p.k) {
                 case 4: kern = seq_kernel<OUT_F32, 1, true, 4>; break;
@@ -187,7 +192,12 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     }
     if (int rc = set_smem(kern, smem)) return rc;
     int per_sm = 1;
-    const int threads = h->seq_threads > 0 ? h->seq_threads : 256;
+    // measured (bench.py --seq-threads): 10 kbp reads with a <= 16 KB histogram run 20 % faster with 4 warps
+    // per CTA (less barrier / priming overhead, occupancy is not the limit); long contigs and the big
+    // histograms want 8 warps.
+    const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
+    const int auto_threads = (mean_len <= 16384 && smem <= 16 * 1024) ? 128 : 256;
+    const int threads = h->seq_threads > 0 ? h->seq_threads : auto_threads;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)h->sm_count * per_sm;
@@ -215,6 +225,8 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
     if (h->force_path != 1) {
         if (!canonical) {
             if (h->ncodes * 4 <= smem_limit) { hist_mode = 0; hist_entries = h->ncodes; }
+        } else if ((h->k & 1) && h->ncodes * 4 > 32 * 1024 && h->ncodes * 2 <= 64 * 1024 && h->dense_odd) {
+            hist_mode = 4; hist_entries = h->ncodes / 2;   // k = 7: dense middle-base index, 32 KB
         } else if (h->ncodes * 4 <= 64 * 1024) {
             hist_mode = 1; hist_entries = h->ncodes;
         } else if (h->dim_canon * 4 <= smem_limit) {
@@ -245,7 +257,9 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         SeqParams qp{};
         qp.bases = d_bases; qp.offsets = d_offsets; qp.n = n; qp.total_bases = total_bases;
         qp.out = d_out; qp.totals = d_totals;
-        qp.rank_full = h->d_rank_full; qp.canon_of_rank = h->d_canon_of_rank; qp.canon_perm = h->d_canon_perm;
+        qp.rank_full = h->d_rank_full;
+        qp.canon_of_rank = hist_mode == 4 ? h->d_mb_of_rank : h->d_canon_of_rank;
+        qp.canon_perm = hist_mode == 4 ? h->d_mb_perm : h->d_canon_perm;
         qp.counter = h->d_counters + 1;
         qp.k = h->k; qp.dim = (uint32_t)dim; qp.hist_entries = (uint32_t)hist_entries;
         qp.norm_mode = norm_mode; qp.canonical = canonical;
@@ -484,6 +498,23 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
                 for (uint32_t e = 0; e < 4; ++e) perm[b * 128 + 4 * l + e] = cor[b * 128 + 32 * e + l];
         CUB(cudaMalloc(&h->d_canon_perm, perm.size() * 4));
         CUB(cudaMemcpy(h->d_canon_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
+        if (k & 1) {  // dense half-size index of seq_kernel mode 4 (see kernels.cuh)
+            const uint32_t midbit = 1u << (2 * (k / 2) + 1);
+            std::vector<uint32_t> mb(cor.size(), 0), mbp(cor.size(), 0);
+            for (uint64_t j = 0; j < h->dim_canon; ++j) {
+                const uint32_t c = cor[j];
+                const uint32_t sel = (c & midbit) ? (uint32_t)rev_comp(c, k) : c;
+                const uint32_t d = (sel & (midbit - 1)) | ((sel >> 1) & ~(midbit - 1));
+                mb[j] = d ^ ((d >> 7) & 31u);   // same bank swizzle as the kernel
+            }
+            for (uint64_t b = 0; b < nblk; ++b)
+                for (uint32_t l = 0; l < 32; ++l)
+                    for (uint32_t e = 0; e < 4; ++e) mbp[b * 128 + 4 * l + e] = mb[b * 128 + 32 * e + l];
+            CUB(cudaMalloc(&h->d_mb_of_rank, mb.size() * 4));
+            CUB(cudaMemcpy(h->d_mb_of_rank, mb.data(), mb.size() * 4, cudaMemcpyHostToDevice));
+            CUB(cudaMalloc(&h->d_mb_perm, mbp.size() * 4));
+            CUB(cudaMemcpy(h->d_mb_perm, mbp.data(), mbp.size() * 4, cudaMemcpyHostToDevice));
+        }
     }
     if (h->ncodes <= (uint64_t)ktb::SHORT_MAX_CODES) {
         std::vector<uint32_t> tc(h->ncodes), tr(h->ncodes);
@@ -535,6 +566,8 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     if (h->d_rank_full) cudaFree(h->d_rank_full);
     if (h->d_canon_of_rank) cudaFree(h->d_canon_of_rank);
     if (h->d_canon_perm) cudaFree(h->d_canon_perm);
+    if (h->d_mb_of_rank) cudaFree(h->d_mb_of_rank);
+    if (h->d_mb_perm) cudaFree(h->d_mb_perm);
     if (h->d_short_tab_canon) cudaFree(h->d_short_tab_canon);
     if (h->d_short_tab_raw) cudaFree(h->d_short_tab_raw);
     if (h->d_counters) cudaFree(h->d_counters);
@@ -585,6 +618,8 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->short_variant = (int)value;
     } else if (!strcmp(key, "short_warps")) {
         h->short_warps = (int)value;
+    } else if (!strcmp(key, "dense_odd")) {
+        h->dense_odd = (int)value;
     } else if (!strcmp(key, "global_wave_bytes")) {
         if (value < 1) return fail(KTB_ERR_ARG, "global_wave_bytes must be positive");
         h->global_wave_bytes = value;

@@ -27,6 +27,9 @@
 #ifndef KTB_SEQ_MINBLOCKS
 #define KTB_SEQ_MINBLOCKS 3
 #endif
+#ifndef KTB_SEQ_MINBLOCKS4
+#define KTB_SEQ_MINBLOCKS4 6
+#endif
 #ifndef KTB_SEQ_FASTPATH
 #define KTB_SEQ_FASTPATH 1
 #endif
@@ -410,6 +413,13 @@ struct SeqParams {
     uint32_t tiles;              // HIST_MODE 3: CTAs cooperating on one sequence (work item = sequence x tile)
 };
 
+// HIST_MODE 4 = canonical, ODD k, dense half-size histogram: the two strands of an odd k-mer differ in the
+//             top bit of their MIDDLE base (m vs 3-m), so "the strand whose middle base is A or C" is a
+//             table-free representative; dropping that bit gives a dense index in [0, 4^k/2).  Half the
+//             shared memory of mode 1 (k=7: 32 KB instead of 64 KB -> twice the CTAs per SM); the gather
+//             table (canon_perm) maps rank -> this index.  Ranks whose representative is the reverse strand
+//             would all fall into one bank (consecutive codes -> reverse complements that differ only in
+//             their HIGH digits), so bits 7..11 of the index are XORed into the bank bits.
 // HIST_MODE 3 = histogram too large for shared memory: atomics (RED) go straight to the zeroed u32 row in
 //             global memory / L2, index rank_full[f] (or f when rank_full is null); no write-out here.
 // HIST_MODE: 0 = raw (index f), 1 = canonical code space (index min(f,r), gather on write-out),
@@ -442,7 +452,7 @@ __device__ __forceinline__ void seq_write_row(uint32_t *hist, typename OutT<OUT>
     // a warp takes ranks {l, 32+l, 64+l, 96+l} of a 128-rank block — consecutive across lanes, so the
     // monotone codes fall into distinct banks — fetched with ONE 128-bit load from a table permuted on
     // the host, and written back with four fully coalesced 32-bit stores.
-    if constexpr (HIST_MODE == 1) {
+    if constexpr (HIST_MODE == 1 || HIST_MODE == 4) {
         const uint32_t nblk = p.dim >> 7;
         const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
         for (uint32_t b = warp; b < nblk; b += nwarps) {
@@ -511,7 +521,8 @@ __device__ __forceinline__ void seq_write_row(uint32_t *hist, typename OutT<OUT>
 // KT: compile-time k (0 = use p.k); the specialised instances fold the window-mask loop and every
 // shift amount into immediates.
 template <int OUT, int HIST_MODE, bool NORM, int KT = 0>
-__global__ void __launch_bounds__(KTB_SEQ_MAXTHREADS, KTB_SEQ_MINBLOCKS) seq_kernel(const SeqParams p) {
+__global__ void __launch_bounds__(KTB_SEQ_MAXTHREADS, (HIST_MODE == 4) ? KTB_SEQ_MINBLOCKS4 : KTB_SEQ_MINBLOCKS)
+seq_kernel(const SeqParams p) {
     extern __shared__ __align__(16) uint32_t hist[];
     __shared__ unsigned long long s_group;
     __shared__ uint32_t s_total[2];  // double-buffered so the reset never races a late reader
@@ -530,6 +541,8 @@ __global__ void __launch_bounds__(KTB_SEQ_MAXTHREADS, KTB_SEQ_MINBLOCKS) seq_ker
 
     const uint32_t k = KT ? (uint32_t)KT : p.k;
     const uint32_t kmask4 = ((k >= 15) ? 0x3FFFFFFFu : ((1u << (2 * k)) - 1u)) << 2;  // code pre-scaled by 4
+    const uint32_t midbit4 = 1u << (2 * (k / 2) + 1 + 2);  // top bit of the middle base (odd k), pre-scaled
+    (void)midbit4;
     using T = typename OutT<OUT>::type;
     T *out = reinterpret_cast<T *>(p.out);
     constexpr uint32_t FULL = 0xffffffffu;
@@ -602,7 +615,7 @@ __global__ void __launch_bounds__(KTB_SEQ_MAXTHREADS, KTB_SEQ_MINBLOCKS) seq_ker
                         mine += __popc(vw);
                         const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
                         uint64_t R64 = 0;
-                        if constexpr (HIST_MODE == 1) {
+                        if constexpr (HIST_MODE == 1 || HIST_MODE == 4) {
                             R64 = ((uint64_t)revcomp_pack(cf) << 32) | revcomp_pack(cf_prev);
                         }
                         uint32_t idx4[16];  // histogram byte offsets
@@ -615,6 +628,11 @@ __global__ void __launch_bounds__(KTB_SEQ_MAXTHREADS, KTB_SEQ_MINBLOCKS) seq_ker
                             } else if constexpr (HIST_MODE == 1) {
                                 const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
                                 idx4[j] = min(f4, r4);
+                            } else if constexpr (HIST_MODE == 4) {
+                                const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
+                                const uint32_t s4 = (f4 & midbit4) ? r4 : f4;          // strand with middle base A/C
+                                const uint32_t d4 = (s4 & (midbit4 - 1u)) | ((s4 >> 1) & ~(midbit4 - 1u));  // drop that (zero) bit
+                                idx4[j] = d4 ^ ((d4 >> 7) & 0x7Cu);   // bank swizzle: see canon_perm / write-out
                             } else if constexpr (HIST_MODE == 2) {
                                 idx4[j] = __ldg(p.rank_full + (f4 >> 2)) << 2;
                             } else {
