@@ -98,6 +98,7 @@ struct ktb_oligo {
     uint32_t *d_canon_perm = nullptr;      // canon_of_rank permuted inside 128-rank blocks (seq_kernel gather)
     uint32_t *d_mb_of_rank = nullptr;      // odd k: rank -> dense middle-base index (seq_kernel mode 4)
     uint32_t *d_mb_perm = nullptr;
+    uint64_t mb_entries = 0;               // histogram words mode 4 needs (dense index + skew)
     uint32_t *d_short_tab_canon = nullptr; // [4^k] (k <= 5): (word byte offset << 22) | 8*(bin&3)
     uint32_t *d_short_tab_raw = nullptr;
     unsigned long long *d_counters = nullptr;  // [4]
@@ -226,7 +227,7 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         if (!canonical) {
             if (h->ncodes * 4 <= smem_limit) { hist_mode = 0; hist_entries = h->ncodes; }
         } else if ((h->k & 1) && h->ncodes * 4 > 32 * 1024 && h->ncodes * 2 <= 64 * 1024 && h->dense_odd) {
-            hist_mode = 4; hist_entries = h->ncodes / 2;   // k = 7: dense middle-base index, 32 KB
+            hist_mode = 4; hist_entries = (h->mb_entries + 3) & ~3ull;   // k = 7: dense middle-base index, 32 KB + skew
         } else if (h->ncodes * 4 <= 64 * 1024) {
             hist_mode = 1; hist_entries = h->ncodes;
         } else if (h->dim_canon * 4 <= smem_limit) {
@@ -505,7 +506,10 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
                 const uint32_t c = cor[j];
                 const uint32_t sel = (c & midbit) ? (uint32_t)rev_comp(c, k) : c;
                 const uint32_t d = (sel & (midbit - 1)) | ((sel >> 1) & ~(midbit - 1));
-                mb[j] = d ^ ((d >> 7) & 31u);   // same bank swizzle as the kernel
+                const uint32_t m = 2 * (k / 2) + 1;                 // bit index of midbit
+                const uint32_t skew = (uint32_t)((4ull << m) >> 9); // words of skew per row, as in the kernel
+                mb[j] = d + (d >> m) * skew;
+                h->mb_entries = std::max<uint64_t>(h->mb_entries, (uint64_t)mb[j] + 1);
             }
             for (uint64_t b = 0; b < nblk; ++b)
                 for (uint32_t l = 0; l < 32; ++l)

@@ -419,7 +419,7 @@ struct SeqParams {
 //             shared memory of mode 1 (k=7: 32 KB instead of 64 KB -> twice the CTAs per SM); the gather
 //             table (canon_perm) maps rank -> this index.  Ranks whose representative is the reverse strand
 //             would all fall into one bank (consecutive codes -> reverse complements that differ only in
-//             their HIGH digits), so bits 7..11 of the index are XORed into the bank bits.
+//             their HIGH digits), so every row of 128 bins is skewed by one more word (k = 7 only).
 // HIST_MODE 3 = histogram too large for shared memory: atomics (RED) go straight to the zeroed u32 row in
 //             global memory / L2, index rank_full[f] (or f when rank_full is null); no write-out here.
 // HIST_MODE: 0 = raw (index f), 1 = canonical code space (index min(f,r), gather on write-out),
@@ -542,7 +542,9 @@ seq_kernel(const SeqParams p) {
     const uint32_t k = KT ? (uint32_t)KT : p.k;
     const uint32_t kmask4 = ((k >= 15) ? 0x3FFFFFFFu : ((1u << (2 * k)) - 1u)) << 2;  // code pre-scaled by 4
     const uint32_t midbit4 = 1u << (2 * (k / 2) + 1 + 2);  // top bit of the middle base (odd k), pre-scaled
-    (void)midbit4;
+    const uint32_t mb_shift = 2 * (k / 2) + 4;              // s4 >> mb_shift = digits above the middle bit
+    const uint32_t mb_mul = midbit4 - 4u * (midbit4 >> 9);  // 2^m*4 minus the skew of 4 bytes per 128 bins
+    (void)midbit4; (void)mb_shift; (void)mb_mul;
     using T = typename OutT<OUT>::type;
     T *out = reinterpret_cast<T *>(p.out);
     constexpr uint32_t FULL = 0xffffffffu;
@@ -631,8 +633,10 @@ seq_kernel(const SeqParams p) {
                             } else if constexpr (HIST_MODE == 4) {
                                 const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
                                 const uint32_t s4 = (f4 & midbit4) ? r4 : f4;          // strand with middle base A/C
-                                const uint32_t d4 = (s4 & (midbit4 - 1u)) | ((s4 >> 1) & ~(midbit4 - 1u));  // drop that (zero) bit
-                                idx4[j] = d4 ^ ((d4 >> 7) & 0x7Cu);   // bank swizzle: see canon_perm / write-out
+                                // drop the (zero) middle bit AND skew rows of 128 bins by one word, in one IMAD:
+                                // s = hi*2^(m+1) + lo  ->  d = hi*2^m + lo,  phys = d + (d >> 7 words) = s - hi*(2^m - 4)
+                                const uint32_t hi = s4 >> mb_shift;
+                                idx4[j] = s4 - hi * mb_mul;
                             } else if constexpr (HIST_MODE == 2) {
                                 idx4[j] = __ldg(p.rank_full + (f4 >> 2)) << 2;
                             } else {
