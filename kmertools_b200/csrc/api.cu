@@ -98,11 +98,13 @@ struct ktb_oligo {
     uint32_t *d_canon_perm = nullptr;      // canon_of_rank permuted inside 128-rank blocks (seq_kernel gather)
     uint32_t *d_mb_of_rank = nullptr;      // odd k: rank -> dense middle-base index (seq_kernel mode 4)
     uint32_t *d_mb_perm = nullptr;
+    uint32_t *d_pk_of_rank = nullptr;      // mode 5: rank -> (16*half) << 24 | byte offset of the packed word
+    uint32_t *d_pk_perm = nullptr;
     uint64_t mb_entries = 0;               // histogram words mode 4 needs (dense index + skew)
     uint32_t *d_short_tab_canon = nullptr; // [4^k] (k <= 5): (word byte offset << 22) | 8*(bin&3)
     uint32_t *d_short_tab_raw = nullptr;
     unsigned long long *d_counters = nullptr;  // [4]
-    DevBuf ws_totals, ws_counts, ws_list;
+    DevBuf ws_totals, ws_counts, ws_list, ws_list2;
     ChunkSet sets[NBUF];
     cudaStream_t aux[2] = {nullptr, nullptr};   // wave overlap in the global-atomic path
     cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
@@ -115,6 +117,7 @@ struct ktb_oligo {
     int short_warps = 0;  // 0 = auto
     int seq_threads = 0;  // 0 = auto (256)
     int dense_odd = 1;    // use seq_kernel mode 4 where it applies
+    int packed16 = 0;     // seq_kernel mode 5 (k = 8 packed code space): measured no faster than mode 2, off by default
     int64_t global_wave_bytes = 64ll << 20;  // rows zeroed + counted together in the global-atomic path (fits L2)
     ktb_stats stats{};
 };
@@ -178,6 +181,7 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     if (hist_mode == 0) kern = nrm ? seq_kernel<OUT, 0, true> : seq_kernel<OUT, 0, false>;
     else if (hist_mode == 1) kern = nrm ? seq_kernel<OUT, 1, true> : seq_kernel<OUT, 1, false>;
     else if (hist_mode == 4) kern = nrm ? seq_kernel<OUT, 4, true> : seq_kernel<OUT, 4, false>;
+    else if (hist_mode == 5) kern = nrm ? seq_kernel<OUT, 5, true> : seq_kernel<OUT, 5, false>;
     else kern = nrm ? seq_kernel<OUT, 2, true> : seq_kernel<OUT, 2, false>;
     if constexpr (OUT == OUT_F32) {
         if (hist_mode == 4 && nrm && p.k == 7) kern = seq_kernel<OUT_F32, 4, true, 7>;   // k folded into immediates for the headline shapes
@@ -197,8 +201,9 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     // per CTA (less barrier / priming overhead, occupancy is not the limit); long contigs and the big
     // histograms want 8 warps.
     const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
-    const int auto_threads = (mean_len <= 16384 && smem <= 16 * 1024) ? 128 : 256;
-    const int threads = h->seq_threads > 0 ? h->seq_threads : auto_threads;
+    const int auto_threads = (hist_mode == 5) ? 1024 : ((mean_len <= 16384 && smem <= 16 * 1024) ? 128 : 256);
+    int threads = h->seq_threads > 0 ? h->seq_threads : auto_threads;
+    if (hist_mode != 2 && hist_mode != 5 && threads > KTB_SEQ_MAXTHREADS) threads = KTB_SEQ_MAXTHREADS;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)h->sm_count * per_sm;
@@ -230,6 +235,8 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
             hist_mode = 4; hist_entries = (h->mb_entries + 3) & ~3ull;   // k = 7: dense middle-base index, 32 KB + skew
         } else if (h->ncodes * 4 <= 64 * 1024) {
             hist_mode = 1; hist_entries = h->ncodes;
+        } else if (h->d_pk_perm && h->packed16) {
+            hist_mode = 5; hist_entries = h->ncodes / 2;   // k = 8: packed 16-bit code space, 128 KB
         } else if (h->dim_canon * 4 <= smem_limit) {
             hist_mode = 2; hist_entries = h->dim_canon;
         }
@@ -267,6 +274,20 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         qp.list = sc.ok ? (const uint32_t *)h->ws_list.p : nullptr;
         qp.list_count = sc.ok ? h->d_counters + 2 : nullptr;
         qp.group_size = SHORT_G;
+        if (hist_mode == 5) {
+            // packed 16-bit counters: sequences with more than 65535 windows come back on out_list and are
+            // redone by the rank-space kernel (mode 2) in a second launch
+            if (int rc = h->ws_list2.ensure(n * 4)) return rc;
+            qp.canon_of_rank = h->d_pk_of_rank; qp.canon_perm = h->d_pk_perm;
+            qp.out_list = (uint32_t *)h->ws_list2.p; qp.out_count = h->d_counters + 3;
+            if (int rc = launch_seq<OUT>(h, qp, 5, st)) return rc;
+            SeqParams q2 = qp;
+            q2.canon_of_rank = h->d_canon_of_rank; q2.canon_perm = h->d_canon_perm;
+            q2.hist_entries = (uint32_t)h->dim_canon;
+            q2.counter = h->d_counters + 0;   // unused by the short kernel for this k, zeroed above
+            q2.list = (const uint32_t *)h->ws_list2.p; q2.list_count = h->d_counters + 3; q2.group_size = 1;
+            return launch_seq<OUT>(h, q2, 2, st);
+        }
         return launch_seq<OUT>(h, qp, hist_mode, st);
     }
 
@@ -499,6 +520,19 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
                 for (uint32_t e = 0; e < 4; ++e) perm[b * 128 + 4 * l + e] = cor[b * 128 + 32 * e + l];
         CUB(cudaMalloc(&h->d_canon_perm, perm.size() * 4));
         CUB(cudaMemcpy(h->d_canon_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
+        if (h->ncodes * 4 > 200 * 1024 && h->ncodes * 2 <= 200 * 1024) {  // packed 16-bit code space (mode 5): k = 8
+            const uint64_t H = h->ncodes / 2;
+            std::vector<uint32_t> pk(cor.size(), 0), pkp(cor.size(), 0);
+            for (uint64_t j = 0; j < h->dim_canon; ++j)
+                pk[j] = (uint32_t)(((cor[j] >= H ? 16u : 0u) << 24) | ((cor[j] & (H - 1)) * 4));
+            for (uint64_t b = 0; b < nblk; ++b)
+                for (uint32_t l = 0; l < 32; ++l)
+                    for (uint32_t e = 0; e < 4; ++e) pkp[b * 128 + 4 * l + e] = pk[b * 128 + 32 * e + l];
+            CUB(cudaMalloc(&h->d_pk_of_rank, pk.size() * 4));
+            CUB(cudaMemcpy(h->d_pk_of_rank, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+            CUB(cudaMalloc(&h->d_pk_perm, pkp.size() * 4));
+            CUB(cudaMemcpy(h->d_pk_perm, pkp.data(), pkp.size() * 4, cudaMemcpyHostToDevice));
+        }
         if (k & 1) {  // dense half-size index of seq_kernel mode 4 (see kernels.cuh)
             const uint32_t midbit = 1u << (2 * (k / 2) + 1);
             std::vector<uint32_t> mb(cor.size(), 0), mbp(cor.size(), 0);
@@ -567,11 +601,14 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     h->ws_totals.release();
     h->ws_counts.release();
     h->ws_list.release();
+    h->ws_list2.release();
     if (h->d_rank_full) cudaFree(h->d_rank_full);
     if (h->d_canon_of_rank) cudaFree(h->d_canon_of_rank);
     if (h->d_canon_perm) cudaFree(h->d_canon_perm);
     if (h->d_mb_of_rank) cudaFree(h->d_mb_of_rank);
     if (h->d_mb_perm) cudaFree(h->d_mb_perm);
+    if (h->d_pk_of_rank) cudaFree(h->d_pk_of_rank);
+    if (h->d_pk_perm) cudaFree(h->d_pk_perm);
     if (h->d_short_tab_canon) cudaFree(h->d_short_tab_canon);
     if (h->d_short_tab_raw) cudaFree(h->d_short_tab_raw);
     if (h->d_counters) cudaFree(h->d_counters);
@@ -622,13 +659,15 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->short_variant = (int)value;
     } else if (!strcmp(key, "short_warps")) {
         h->short_warps = (int)value;
+    } else if (!strcmp(key, "packed16")) {
+        h->packed16 = (int)value;
     } else if (!strcmp(key, "dense_odd")) {
         h->dense_odd = (int)value;
     } else if (!strcmp(key, "global_wave_bytes")) {
         if (value < 1) return fail(KTB_ERR_ARG, "global_wave_bytes must be positive");
         h->global_wave_bytes = value;
     } else if (!strcmp(key, "seq_threads")) {
-        if (value != 0 && (value < 32 || value > KTB_SEQ_MAXTHREADS || value % 32)) return fail(KTB_ERR_ARG, "seq_threads must be a multiple of 32 in 32..%d", KTB_SEQ_MAXTHREADS);
+        if (value != 0 && (value < 32 || value > 1024 || value % 32)) return fail(KTB_ERR_ARG, "seq_threads must be a multiple of 32 in 32..1024");
         h->seq_threads = (int)value;
     } else {
         return fail(KTB_ERR_ARG, "unknown option '%s'", key);

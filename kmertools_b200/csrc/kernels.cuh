@@ -411,8 +411,14 @@ struct SeqParams {
     uint64_t seq_base;           // HIST_MODE 3: first sequence of this wave
     uint64_t seq_count;          // HIST_MODE 3: sequences in this wave
     uint32_t tiles;              // HIST_MODE 3: CTAs cooperating on one sequence (work item = sequence x tile)
+    uint32_t *out_list;          // HIST_MODE 5: sequences with > 65535 windows are appended here (next launch)
+    unsigned long long *out_count;
 };
 
+// HIST_MODE 5 = code space with 16-bit counters packed two to a word (k = 8: 4^8 codes in 128 KB, no rank
+//             table look-ups at all; k = 8 canonical in rank space needed one random L2 access per k-mer and
+//             ran at one look-up per cycle per SM).  Code c lives in word c & (H-1), half c >> log2(H).
+//             Sequences with more than 65535 windows are passed on to the next launch (out_list).
 // HIST_MODE 4 = canonical, ODD k, dense half-size histogram: the two strands of an odd k-mer differ in the
 //             top bit of their MIDDLE base (m vs 3-m), so "the strand whose middle base is A or C" is a
 //             table-free representative; dropping that bit gives a dense index in [0, 4^k/2).  Half the
@@ -452,6 +458,31 @@ __device__ __forceinline__ void seq_write_row(uint32_t *hist, typename OutT<OUT>
     // a warp takes ranks {l, 32+l, 64+l, 96+l} of a 128-rank block — consecutive across lanes, so the
     // monotone codes fall into distinct banks — fetched with ONE 128-bit load from a table permuted on
     // the host, and written back with four fully coalesced 32-bit stores.
+    if constexpr (HIST_MODE == 5) {
+        // packed 16-bit counters: canon_perm entries are (16 * half) << 24 | byte offset of the word; gather
+        // (lanes take consecutive ranks), convert, store; the histogram is zeroed in bulk afterwards because
+        // two codes share a word.
+        const uint32_t nblk = p.dim >> 7;
+        const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+        const uint8_t *hb = reinterpret_cast<const uint8_t *>(hist);
+        auto cnt_of = [&](uint32_t e) -> uint32_t {
+            return (*reinterpret_cast<const uint32_t *>(hb + (e & 0xFFFFFFu)) >> (e >> 24)) & 0xFFFFu;
+        };
+        for (uint32_t b = warp; b < nblk; b += nwarps) {
+            const uint4 cc = __ldg(reinterpret_cast<const uint4 *>(p.canon_perm + (b << 7)) + lane);
+            T *dst = row + (b << 7) + lane;
+            dst[0] = cvt_count<OUT, NORM, SMALL>(cnt_of(cc.x), dF, rinv, dD);
+            dst[32] = cvt_count<OUT, NORM, SMALL>(cnt_of(cc.y), dF, rinv, dD);
+            dst[64] = cvt_count<OUT, NORM, SMALL>(cnt_of(cc.z), dF, rinv, dD);
+            dst[96] = cvt_count<OUT, NORM, SMALL>(cnt_of(cc.w), dF, rinv, dD);
+        }
+        for (uint32_t j = (nblk << 7) + tid; j < p.dim; j += blockDim.x)
+            row[j] = cvt_count<OUT, NORM, SMALL>(cnt_of(__ldg(p.canon_of_rank + j)), dF, rinv, dD);
+        __syncthreads();
+        uint4 *hz = reinterpret_cast<uint4 *>(hist);
+        for (uint32_t i = tid; i < p.hist_entries / 4; i += blockDim.x) hz[i] = make_uint4(0, 0, 0, 0);
+        return;
+    }
     if constexpr (HIST_MODE == 1 || HIST_MODE == 4) {
         const uint32_t nblk = p.dim >> 7;
         const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -521,7 +552,8 @@ __device__ __forceinline__ void seq_write_row(uint32_t *hist, typename OutT<OUT>
 // KT: compile-time k (0 = use p.k); the specialised instances fold the window-mask loop and every
 // shift amount into immediates.
 template <int OUT, int HIST_MODE, bool NORM, int KT = 0>
-__global__ void __launch_bounds__(KTB_SEQ_MAXTHREADS, (HIST_MODE == 4) ? KTB_SEQ_MINBLOCKS4 : KTB_SEQ_MINBLOCKS)
+__global__ void __launch_bounds__((HIST_MODE == 2 || HIST_MODE == 5) ? 1024 : KTB_SEQ_MAXTHREADS,
+                                  (HIST_MODE == 2 || HIST_MODE == 5) ? 1 : ((HIST_MODE == 4) ? KTB_SEQ_MINBLOCKS4 : KTB_SEQ_MINBLOCKS))
 seq_kernel(const SeqParams p) {
     extern __shared__ __align__(16) uint32_t hist[];
     __shared__ unsigned long long s_group;
@@ -545,6 +577,9 @@ seq_kernel(const SeqParams p) {
     const uint32_t mb_shift = 2 * (k / 2) + 4;              // s4 >> mb_shift = digits above the middle bit
     const uint32_t mb_mul = midbit4 - 4u * (midbit4 >> 9);  // 2^m*4 minus the skew of 4 bytes per 128 bins
     (void)midbit4; (void)mb_shift; (void)mb_mul;
+    const uint32_t pk_mask4 = p.hist_entries * 4u - 1u;           // mode 5: byte offset of the word
+    const uint32_t pk_shift = 31u - __clz(p.hist_entries * 4u) - 4u;  // (c4 >> pk_shift) & 16 = 16 * upper-half bit
+    (void)pk_mask4; (void)pk_shift;
     using T = typename OutT<OUT>::type;
     T *out = reinterpret_cast<T *>(p.out);
     constexpr uint32_t FULL = 0xffffffffu;
@@ -575,6 +610,12 @@ seq_kernel(const SeqParams p) {
             const uint64_t s0 = p.offsets[seq];
             const uint64_t s1 = p.offsets[seq + 1];
             uint32_t mine = 0;  // valid windows counted by this thread
+            if constexpr (HIST_MODE == 5) {
+                if (s1 - s0 > 65535ull + k - 1) {   // a 16-bit counter could overflow: leave it to the next launch
+                    if (tid == 0) p.out_list[atomicAdd(p.out_count, 1ULL)] = (uint32_t)seq;
+                    continue;                        // uniform for the CTA; no barrier skipped inside this iteration
+                }
+            }
             if (s1 - s0 >= k) {
                 const uint64_t cbase = s0 >> 4;                                     // absolute index of chunk 0
                 const uint32_t nch = (uint32_t)(((s1 - 1) >> 4) - cbase) + 1u;      // chunks touching the sequence
@@ -617,7 +658,7 @@ seq_kernel(const SeqParams p) {
                         mine += __popc(vw);
                         const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
                         uint64_t R64 = 0;
-                        if constexpr (HIST_MODE == 1 || HIST_MODE == 4) {
+                        if constexpr (HIST_MODE == 1 || HIST_MODE == 4 || HIST_MODE == 5) {
                             R64 = ((uint64_t)revcomp_pack(cf) << 32) | revcomp_pack(cf_prev);
                         }
                         uint32_t idx4[16];  // histogram byte offsets
@@ -637,6 +678,9 @@ seq_kernel(const SeqParams p) {
                                 // s = hi*2^(m+1) + lo  ->  d = hi*2^m + lo,  phys = d + (d >> 7 words) = s - hi*(2^m - 4)
                                 const uint32_t hi = s4 >> mb_shift;
                                 idx4[j] = s4 - hi * mb_mul;
+                            } else if constexpr (HIST_MODE == 5) {
+                                const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
+                                idx4[j] = p.canonical ? min(f4, r4) : f4;   // unpacked below
                             } else if constexpr (HIST_MODE == 2) {
                                 idx4[j] = __ldg(p.rank_full + (f4 >> 2)) << 2;
                             } else {
@@ -648,6 +692,17 @@ seq_kernel(const SeqParams p) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
                                 if (vw & (1u << (15 - j))) atomicAdd(reinterpret_cast<uint32_t *>(grow + idx4[j]), 1u);
+                            continue;
+                        }
+                        if constexpr (HIST_MODE == 5) {
+                            const bool all16 = __all_sync(FULL, vw == 0xFFFFu);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const uint32_t c4 = idx4[j];
+                                const uint32_t one = all16 ? 1u : ((vw >> (15 - j)) & 1u);
+                                atomicAdd(reinterpret_cast<uint32_t *>(hbytes + (c4 & pk_mask4)),
+                                          one << ((c4 >> pk_shift) & 16u));
+                            }
                             continue;
                         }
                         if (KTB_SEQ_FASTPATH && __all_sync(FULL, vw == 0xFFFFu)) {

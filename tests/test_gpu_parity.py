@@ -23,7 +23,7 @@ def comp(k):
 
 def check(k, bases, offsets, mins=True, norm_mode=NORM_CLI, dtype=np.float32, what="", **opts):
     oc = comp(k)
-    for key in ("force_path", "short_variant"):
+    for key in ("force_path", "short_variant", "packed16"):
         oc.set_option(key, opts.get(key, 0))
     n = len(offsets) - 1
     totals = np.zeros(n, dtype=np.uint64)
@@ -31,7 +31,7 @@ def check(k, bases, offsets, mins=True, norm_mode=NORM_CLI, dtype=np.float32, wh
     want, wtot = O.vectorise_batch(bases, offsets, k, mins, norm_mode)
     assert np.array_equal(totals, wtot), f"{what}: totals differ"
     assert_rows_equal(got, want, dtype, what)
-    for key in ("force_path", "short_variant"):
+    for key in ("force_path", "short_variant", "packed16"):
         oc.set_option(key, 0)
     return got
 
@@ -147,6 +147,19 @@ def test_medium_and_long_sequences(k):
     check(k, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"k{k} counts")
     check(k, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, what=f"k{k} f32")
     check(k, bases, offsets, mins=False, norm_mode=NORM_CLI, dtype=np.float64, what=f"k{k} raw f64") if k < 8 else None
+
+
+def test_k8_packed16_variant_with_overflow_fallback():
+    """seq_kernel mode 5 (16-bit counters packed in code space): sequences with more than 65535 windows must
+    come back through the second launch; a homopolymer drives one counter to its limit."""
+    rng = np.random.default_rng(88)
+    lengths = np.r_[rng.integers(0, 5000, size=30), [65535 + 7, 65535 + 8, 70000, 200000, 65542]]
+    bases, offsets = random_batch(rng, lengths, noise=0.001, n_runs=0.3)
+    bases[int(offsets[30]):int(offsets[31])] = ord("A")     # 65535 windows of AAAAAAAA: exactly fits
+    bases[int(offsets[31]):int(offsets[32])] = ord("T")     # 65536 windows: must take the fallback
+    check(8, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, packed16=1, what="k8 packed counts")
+    check(8, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, packed16=1, what="k8 packed f32")
+    check(8, bases, offsets, norm_mode=NORM_CLI, dtype=np.float64, packed16=1, what="k8 packed f64")
 
 
 @pytest.mark.parametrize("k", [9, 10])
