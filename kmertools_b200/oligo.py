@@ -148,6 +148,39 @@ class OligoComputer:
                                                  code, out.ctypes.data if n else None, tptr))
         return out
 
+    def vectorise_tensors(self, bases, offsets, norm_mode: int = NORM_CLI, mins: bool = True, dtype=None,
+                          out=None, totals=None):
+        """Zero-copy surface for torch users ("next" row N4): `bases` (uint8) and `offsets` (int64, n+1) are
+        CUDA tensors on this handle's GPU, the result is a CUDA tensor (n x dim) — nothing crosses PCIe.
+        The work is enqueued on torch's current stream."""
+        import torch
+        assert bases.is_cuda and offsets.is_cuda and bases.dtype == torch.uint8 and offsets.dtype == torch.int64
+        assert bases.device.index == self.device and bases.is_contiguous() and offsets.is_contiguous()
+        dtype = dtype or torch.float32
+        code = {torch.int32: OUT_U32, torch.float32: OUT_F32, torch.float64: OUT_F64}[dtype]
+        n = offsets.numel() - 1
+        if out is None:
+            out = torch.empty((n, self.dim(mins)), dtype=dtype, device=bases.device)
+        assert out.is_cuda and out.dtype == dtype and out.is_contiguous() and tuple(out.shape) == (n, self.dim(mins))
+        total = int(offsets[-1]) if n >= 0 and offsets.numel() else 0
+        tptr = None
+        if totals is not None:
+            assert totals.is_cuda and totals.dtype == torch.int64 and totals.numel() == n
+            tptr = totals.data_ptr()
+        stream = torch.cuda.current_stream(bases.device).cuda_stream
+        self.vectorise_device(bases.data_ptr() if total else 0, offsets.data_ptr(), n, total, out.data_ptr() if n else 0,
+                              norm_mode=norm_mode, mins=mins, out_dtype=code, d_totals=tptr, stream=stream)
+        return out
+
+    def vectorise_batch_tensor(self, seqs: Sequence, norm: bool = True, mins: bool = True, dtype=None):
+        """vectorise_batch with the rows left on the GPU as a torch tensor (reference semantics, PY norm)."""
+        import torch
+        bases, offsets = _pack(seqs)
+        dev = torch.device("cuda", self.device)
+        tb = torch.from_numpy(bases.copy() if bases.size else np.zeros(16, np.uint8)).to(dev)
+        to = torch.from_numpy(offsets.astype(np.int64)).to(dev)
+        return self.vectorise_tensors(tb, to, NORM_PY if norm else NORM_COUNTS, mins, dtype)
+
     def vectorise_device(self, d_bases: int, d_offsets: int, n: int, total_bases: int, d_out: int,
                          norm_mode: int = NORM_CLI, mins: bool = True, out_dtype: int = OUT_F32,
                          d_totals: int | None = None, stream: int | None = None) -> None:

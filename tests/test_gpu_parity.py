@@ -240,3 +240,17 @@ def test_device_entry_point_with_torch_tensors():
     # size-independent property: every row sums to 1 (or 0)
     s = out.sum(dim=1)
     assert torch.all((s - 1).abs() < 1e-4)
+
+
+def test_torch_tensor_surface():
+    import torch
+    oc = comp(4)
+    seqs = [b"ACGTTGCANNACGT" * 5, b"", b"acgtacgtacgtaaaaccc", b"GGGTGATGGCCGCTGCCGATGGCGTCAAATCCCACCAAGTTACC"]
+    t = oc.vectorise_batch_tensor(seqs)
+    assert t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == (4, 136)
+    bases, offsets = O.pack(seqs)
+    want, _ = O.vectorise_batch(bases, offsets, 4, True, NORM_PY)
+    torch.cuda.synchronize()
+    assert_rows_equal(t.cpu().numpy(), want, np.float32, "tensor surface")
+    c = oc.vectorise_batch_tensor(seqs, norm=False, dtype=torch.int32)
+    assert np.array_equal(c.cpu().numpy().astype(np.uint32), O.vectorise_batch(bases, offsets, 4, True, 0)[0].astype(np.uint32))
