@@ -157,6 +157,11 @@ typedef struct ktb_file_stats {
 
 int ktb_comp_oligo_file(const ktb_file_opts *opts, ktb_file_stats *stats /* optional */);
 
+/* `kmertools comp cgr -k K` (k-mer mode; OligoCgrComputer, composition/src/oligocgr.rs:63-163): the same
+ * canonical histogram, printed as "(x,y,freq)" triples where (x,y) is the fixed chaos-game point of the
+ * column's k-mer in a vecsize x vecsize square.  Uses in_path, out_path, k, norm, device of `opts`. */
+int ktb_comp_cgr_file(const ktb_file_opts *opts, int vecsize, ktb_file_stats *stats /* optional */);
+
 /* Loads a whole FASTA/FASTQ(.gz) file into packed buffers (malloc'ed; release with ktb_free).
  * sniff != 0: format from the first byte, else from the extension. */
 int ktb_fastx_load(const char *path, int sniff, uint8_t **bases, uint64_t **offsets, uint64_t *n);

@@ -24,10 +24,48 @@ static void usage() {
             "      --device <N>       CUDA device ordinal [default: 0]\n");
 }
 
+// `kmertools comp cgr -k K ...` (k-mer mode of kmertools/src/args.rs:105-128,264-283)
+static int main_cgr(int argc, char **argv) {
+    ktb_file_opts o{};
+    std::string in, out;
+    o.k = 0; o.canonical = 1; o.norm = 1; o.delim = ' '; o.device = 0;
+    long vec = -1;
+    for (int i = 3; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto val = [&](const char *name) -> const char * {
+            if (i + 1 >= argc) { fprintf(stderr, "error: a value is required for '%s'\n", name); exit(2); }
+            return argv[++i];
+        };
+        if (a == "-i" || a == "--input") in = val("--input");
+        else if (a == "-o" || a == "--output") out = val("--output");
+        else if (a == "-c" || a == "--counts") o.norm = 0;
+        else if (a == "-k" || a == "--k-size") o.k = atoi(val("--k-size"));
+        else if (a == "-v" || a == "--vec-size") vec = atol(val("--vec-size"));
+        else if (a == "-t" || a == "--threads") o.threads = atoi(val("--threads"));
+        else if (a == "--device") o.device = atoi(val("--device"));
+        else { fprintf(stderr, "error: unexpected argument '%s' found\n", a.c_str()); return 2; }
+    }
+    if (in.empty() || out.empty()) { fprintf(stderr, "error: --input and --output are required\n"); return 2; }
+    if (o.k == 0) {
+        fprintf(stderr, "error: whole-sequence CGR (no -k) is outside this build's scope; use -k 3..7 for k-mer mode\n");
+        return 2;
+    }
+    if (o.k < 3 || o.k > 7) {
+        fprintf(stderr, "error: invalid value '%d' for '--k-size <K_SIZE>': %d is not in 3..=7\n", o.k, o.k);
+        return 2;
+    }
+    if (vec < 0) vec = (long)(o.k * o.k);   // (k as f64).powf(4.0).powf(0.5) as u64
+    o.in_path = in.c_str();
+    o.out_path = out.c_str();
+    if (ktb_comp_cgr_file(&o, (int)vec, nullptr) != KTB_OK) fprintf(stderr, "Error: %s\n", ktb_last_error());
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc >= 3 && !strcmp(argv[1], "comp") && !strcmp(argv[2], "cgr")) return main_cgr(argc, argv);
     if (argc < 3 || strcmp(argv[1], "comp") != 0 || strcmp(argv[2], "oligo") != 0) {
         if (argc >= 2 && (!strcmp(argv[1], "-h") || !strcmp(argv[1], "--help"))) { usage(); return 0; }
-        fprintf(stderr, "error: this build provides only `kmertools comp oligo` (GPU oligo-frequency-vector path)\n");
+        fprintf(stderr, "error: this build provides only `kmertools comp oligo` and `kmertools comp cgr -k` (GPU oligo path)\n");
         usage();
         return 2;
     }

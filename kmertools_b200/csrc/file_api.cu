@@ -6,6 +6,7 @@
 #include "fastx.h"
 #include "textfmt.cuh"
 
+#include <charconv>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -93,6 +94,63 @@ size_t format_counts_rows(const uint32_t *counts, uint64_t n, uint32_t dim, char
     return w;
 }
 
+
+// Rust's `{}` for f64: shortest digits that round-trip, never an exponent (std::to_chars fixed does the same)
+inline char *put_f64(char *o, double v) {
+    auto r = std::to_chars(o, o + 400, v, std::chars_format::fixed);
+    return r.ptr;
+}
+
+// composition/src/oligocgr.rs:123-143,165-190: every canonical k-mer gets a fixed point, the midpoint
+// recurrence from the centre towards the corner of each base (A (0,0), T (v,0), G (v,v), C (0,v))
+void cgr_prefixes(const ktb_oligo *h, int k, uint64_t dim, double vecsize, std::vector<std::string> *pref) {
+    std::vector<char> hb(dim * k);
+    ktb_oligo_header(h, 1, hb.data(), hb.size());
+    pref->resize(dim);
+    for (uint64_t j = 0; j < dim; ++j) {
+        double x = vecsize / 2.0, y = vecsize / 2.0;
+        for (int i = 0; i < k; ++i) {
+            double cx = 0, cy = 0;
+            switch (hb[j * k + i]) {
+                case 'A': cx = 0; cy = 0; break;
+                case 'T': cx = vecsize; cy = 0; break;
+                case 'G': cx = vecsize; cy = vecsize; break;
+                default: cx = 0; cy = vecsize; break;  // 'C'
+            }
+            x = (cx + x) / 2.0;
+            y = (cy + y) / 2.0;
+        }
+        char buf[900];
+        char *o = buf;
+        *o++ = '(';
+        o = put_f64(o, x);
+        *o++ = ',';
+        o = put_f64(o, y);
+        *o++ = ',';
+        (*pref)[j].assign(buf, o);
+    }
+}
+
+// rows -> "(x,y,freq) (x,y,freq) ...\n" (oligocgr.rs:88-101)
+size_t format_cgr_rows(const void *rows, bool norm, uint64_t n, uint32_t dim, const std::vector<std::string> &pref,
+                       std::vector<char> *out) {
+    size_t plen = 0;
+    for (auto &p : pref) plen += p.size();
+    out->resize((size_t)n * (plen + (size_t)dim * 420) + 16);
+    char *o = out->data();
+    for (uint64_t i = 0; i < n; ++i) {
+        for (uint32_t j = 0; j < dim; ++j) {
+            memcpy(o, pref[j].data(), pref[j].size());
+            o += pref[j].size();
+            if (norm) o = put_f64(o, ((const double *)rows)[i * dim + j]);
+            else o = put_f64(o, (double)((const uint32_t *)rows)[i * dim + j]);
+            *o++ = ')';
+            *o++ = (j + 1 == dim) ? '\n' : ' ';
+        }
+    }
+    return (size_t)(o - out->data());
+}
+
 }  // namespace
 
 extern "C" {
@@ -138,7 +196,8 @@ int ktb_fastx_load(const char *path, int sniff, uint8_t **bases, uint64_t **offs
     return KTB_OK;
 }
 
-int ktb_comp_oligo_file(const ktb_file_opts *o, ktb_file_stats *stats) {
+static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsize) {
+    const bool cgr = cgr_vecsize > 0;
     const double t_start = now_ms();
     if (!o || !o->in_path || !o->out_path) return ktb_internal_fail(KTB_ERR_ARG, "null argument");
     ktb_file_stats st{};
@@ -150,7 +209,7 @@ int ktb_comp_oligo_file(const ktb_file_opts *o, ktb_file_stats *stats) {
     std::string err;
     if (!src.open(in, &err)) return ktb_internal_fail(KTB_ERR_IO, err.c_str());
     ktb::SeqFormat fmt;
-    if (in == "-" || !norm) {
+    if (in == "-" || !norm || cgr) {   // oligocgr.rs:64-72 always sniffs
         fmt = (src.peek_first_byte() == '>') ? ktb::SeqFormat::Fasta : ktb::SeqFormat::Fastq;
     } else if (!ktb::format_from_path(in, &fmt)) {
         return ktb_internal_fail(KTB_ERR_IO, "unknown sequence file extension (expected .fa/.fasta/.fna/.fq/.fastq[.gz])");
@@ -160,7 +219,7 @@ int ktb_comp_oligo_file(const ktb_file_opts *o, ktb_file_stats *stats) {
     ktb_oligo *h = nullptr;
     if (int rc = ktb_oligo_create(o->k, o->device, &h)) return rc;
     struct Guard { ktb_oligo *h; ~Guard() { ktb_oligo_destroy(h); } } guard{h};
-    const uint64_t dim = ktb_oligo_dim(h, o->canonical);
+    const uint64_t dim = ktb_oligo_dim(h, cgr ? 1 : o->canonical);
 
     FILE *fo = fopen(o->out_path, "wb");
     if (!fo) return ktb_internal_fail(KTB_ERR_IO, (std::string("Unable to write to file: ") + o->out_path).c_str());
@@ -168,7 +227,9 @@ int ktb_comp_oligo_file(const ktb_file_opts *o, ktb_file_stats *stats) {
     std::vector<char> iobuf(8u << 20);
     setvbuf(fo, iobuf.data(), _IOFBF, iobuf.size());
 
-    if (o->header) {  // get_header().join(delim) + "\n", oligo.rs:114-117
+    std::vector<std::string> cgr_pref;
+    if (cgr) cgr_prefixes(h, o->k, dim, (double)cgr_vecsize, &cgr_pref);
+    if (o->header && !cgr) {  // get_header().join(delim) + "\n", oligo.rs:114-117
         std::vector<char> hb(dim * o->k);
         if (int rc = ktb_oligo_header(h, o->canonical, hb.data(), hb.size())) return rc;
         std::string line;
@@ -183,7 +244,8 @@ int ktb_comp_oligo_file(const ktb_file_opts *o, ktb_file_stats *stats) {
     }
 
     // ---- batch geometry
-    const size_t out_per_row = norm ? dim * 9 : dim * 4;
+    const bool gpu_text = norm && !cgr;          // fixed-width rows are formatted on the GPU
+    const size_t out_per_row = gpu_text ? dim * 9 : ((cgr && norm) ? dim * 8 : dim * 4);
     const size_t OUT_CAP = 256u << 20;
     const size_t max_records = std::max<size_t>(1, std::min<size_t>(OUT_CAP / out_per_row, 4u << 20));
     size_t bases_cap = 128u << 20;
@@ -203,9 +265,13 @@ int ktb_comp_oligo_file(const ktb_file_opts *o, ktb_file_stats *stats) {
         const double t1 = now_ms();
         st.gpu_wait_ms += t1 - t0;
         size_t w;
-        if (norm) {
+        if (gpu_text) {
             w = fwrite(s.h_out.p, 1, s.out_bytes, fo);
             if (w != s.out_bytes) return ktb_internal_fail(KTB_ERR_IO, "short write");
+        } else if (cgr) {
+            const size_t len = format_cgr_rows(s.h_out.p, norm, s.n, (uint32_t)dim, cgr_pref, &text);
+            w = fwrite(text.data(), 1, len, fo);
+            if (w != len) return ktb_internal_fail(KTB_ERR_IO, "short write");
         } else {
             const size_t len = format_counts_rows((const uint32_t *)s.h_out.p, s.n, (uint32_t)dim, o->delim, &text);
             w = fwrite(text.data(), 1, len, fo);
@@ -249,18 +315,20 @@ int ktb_comp_oligo_file(const ktb_file_opts *o, ktb_file_stats *stats) {
         memcpy(s.h_offsets.p, offs.data(), (n + 1) * 8);
         s.out_bytes = n * out_per_row;
         if (!s.h_out.ensure(s.out_bytes) || !s.d_bases.ensure(used + 64) || !s.d_offsets.ensure((n + 1) * 8) ||
-            !s.d_counts.ensure(n * dim * 4) || !s.d_totals.ensure(n * 8) || (norm && !s.d_text.ensure(n * dim * 9)))
+            !s.d_counts.ensure(n * dim * 8) || !s.d_totals.ensure(n * 8) || (gpu_text && !s.d_text.ensure(n * dim * 9)))
             return ktb_internal_fail(KTB_ERR_NOMEM, "buffer allocation failed");
         cudaMemcpyAsync(s.d_bases.p, s.h_bases.p, used, cudaMemcpyHostToDevice, s.stream);
         cudaMemcpyAsync(s.d_offsets.p, s.h_offsets.p, (n + 1) * 8, cudaMemcpyHostToDevice, s.stream);
         const uint64_t l0 = ktb_internal_launches(h);
         (void)l0;
+        const bool f64rows = cgr && norm;   // CGR prints the f64 quotient itself ("{}")
         if (int rc = ktb_internal_dispatch(h, (const uint8_t *)s.d_bases.p, (const uint64_t *)s.d_offsets.p, n, used,
-                                           o->canonical, KTB_NORM_COUNTS, KTB_OUT_U32, s.d_counts.p,
+                                           cgr ? 1 : o->canonical, f64rows ? KTB_NORM_CLI : KTB_NORM_COUNTS,
+                                           f64rows ? KTB_OUT_F64 : KTB_OUT_U32, s.d_counts.p,
                                            (uint64_t *)s.d_totals.p, s.stream))
             return rc;
         launches += ktb_internal_launches(h);
-        if (norm) {
+        if (gpu_text) {
             const uint64_t nel = n * dim;
             uint64_t grid = (nel + 255) / 256;
             const uint64_t cap = (uint64_t)ktb_internal_sms(h) * 16;
@@ -286,6 +354,13 @@ int ktb_comp_oligo_file(const ktb_file_opts *o, ktb_file_stats *stats) {
     st.total_ms = now_ms() - t_start;
     if (stats) *stats = st;
     return KTB_OK;
+}
+
+int ktb_comp_oligo_file(const ktb_file_opts *o, ktb_file_stats *stats) { return run_file(o, stats, 0); }
+
+int ktb_comp_cgr_file(const ktb_file_opts *o, int vecsize, ktb_file_stats *stats) {
+    if (vecsize < 1) return ktb_internal_fail(KTB_ERR_ARG, "vecsize must be positive");
+    return run_file(o, stats, vecsize);
 }
 
 }  // extern "C"

@@ -42,6 +42,19 @@ def comp_oligo(in_path, out_path, k: int = 3, counts: bool = False, raw_count: b
     return {f: getattr(st, f) for f, _ in st._fields_}
 
 
+def comp_cgr(in_path, out_path, k: int, counts: bool = False, vec_size: int | None = None, threads: int = 0,
+             device: int = 0) -> dict:
+    """`kmertools comp cgr -i in -o out -k K [-c] [-v N]` (k-mer mode, kmertools/src/args.rs:105-128,264-283)."""
+    L = _lib.load()
+    if vec_size is None:
+        vec_size = int((float(k) ** 4.0) ** 0.5)   # args.rs:268-271
+    o = _lib.FileOpts(os.fsencode(str(in_path)), os.fsencode(str(out_path)), int(k), 1, int(not counts), b" ", 0,
+                      int(threads), int(device))
+    st = _lib.FileStats()
+    _lib.check(L.ktb_comp_cgr_file(C.byref(o), int(vec_size), C.byref(st)))
+    return {f: getattr(st, f) for f, _ in st._fields_}
+
+
 def format6(q: float) -> str:
     """Host build of the GPU text formatter: Rust's format!("{:.6}", q) for q in [0, 1]."""
     buf = C.create_string_buffer(9)

@@ -91,3 +91,30 @@ def test_python_driver_and_many_batches(tmp_path):
     rows, _ = O.vectorise_batch(arr.reshape(-1).copy(), np.arange(n + 1, dtype=np.uint64) * 100, 7, True, 1)
     for i in (0, 1, 3639, 3640, 3641, 3642, n // 2, n - 1):
         assert data[i * 73728:(i + 1) * 73728] == O.format_rows(rows[i:i + 1], True), i
+
+
+def test_comp_cgr_kmer_mode_golden(golden, tmp_path):
+    """oligo_cgr_complete_unnorm_test (composition/src/oligocgr.rs:219-238): reads.fq, k=4, vecsize 16, counts."""
+    out = tmp_path / "o.cgr"
+    r = subprocess.run([str(BIN), "comp", "cgr", "-i", str(golden / "reads.fq"), "-o", str(out), "-k", "4", "-c"],
+                       capture_output=True)
+    assert r.returncode == 0 and r.stderr == b"", r.stderr
+    assert out.read_bytes() == (golden / "expected_reads.k4.cgr").read_bytes()
+
+
+def test_comp_cgr_normalised_values(golden, tmp_path):
+    """Normalised k-mer CGR: freq is Rust's `{}` of the f64 quotient = Python's repr (shortest round-trip)."""
+    from kmertools_b200 import io as kio
+    out = tmp_path / "o.cgr"
+    kio.comp_cgr(golden / "reads.fa", out, k=4)
+    seqs = [s for _, s in O.read_fastx(golden / "reads.fa")]
+    rows, _ = O.vectorise_batch(*O.pack(seqs), 4, True, 1)
+    lines = out.read_text().splitlines()
+    assert len(lines) == 2
+    for ln, row in zip(lines, rows):
+        trip = [t.strip("()").split(",") for t in ln.split(" ")]
+        assert len(trip) == 136
+        assert trip[0][:2] == ["0.5", "0.5"]                 # AAAA -> (0.5, 0.5), oligocgr.rs:205-206
+        for (x, y, f), want in zip(trip, row):
+            w = repr(float(want))
+            assert f == (w[:-2] if w.endswith(".0") else w), (f, w)
