@@ -207,8 +207,8 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)h->sm_count * per_sm;
-    const uint64_t ngroups = (p.n + p.group_size - 1) / p.group_size;
-    if (grid > ngroups) grid = ngroups;
+    const uint64_t nitems = ((p.n + p.group_size - 1) / p.group_size) * p.group_size;   // one sequence per item
+    if (grid > nitems) grid = nitems;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, threads, smem, st>>>(p);
     CU(cudaGetLastError());

@@ -563,8 +563,10 @@ seq_kernel(const SeqParams p) {
     const int lane = tid & 31;
     const uint32_t warp = tid >> 5;
     const uint32_t nwarps = blockDim.x >> 5;
+    // work item = one sequence: (sequence of the wave, tile) in mode 3, else (group, index within the group) —
+    // a whole group of 16 contigs per item left the last CTAs with megabases of work (19 % tail on config 4)
     const uint64_t nitems = (HIST_MODE == 3) ? p.seq_count * p.tiles
-                            : (p.list ? (uint64_t)*p.list_count : (p.n + p.group_size - 1) / p.group_size);
+                            : (p.list ? (uint64_t)*p.list_count : (p.n + p.group_size - 1) / p.group_size) * p.group_size;
     if ((uint64_t)blockIdx.x >= nitems) return;  // nothing for this CTA (e.g. short_kernel took everything)
     for (uint32_t i = tid; i < p.hist_entries; i += blockDim.x) hist[i] = 0;
     if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
@@ -600,9 +602,10 @@ seq_kernel(const SeqParams p) {
             tile = (uint32_t)(item % tiles);
             nseq = 1;
         } else {
-            const uint64_t g = p.list ? (uint64_t)p.list[item] : (uint64_t)item;
-            i0 = g * (uint64_t)p.group_size;
-            nseq = (uint32_t)min((unsigned long long)p.group_size, (unsigned long long)(p.n - i0));
+            const uint64_t gi = item / p.group_size;
+            const uint64_t g = p.list ? (uint64_t)p.list[gi] : gi;
+            i0 = g * (uint64_t)p.group_size + (item - gi * p.group_size);
+            nseq = (i0 < p.n) ? 1u : 0u;
         }
 
         for (uint32_t si = 0; si < nseq; ++si) {
