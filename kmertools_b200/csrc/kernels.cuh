@@ -638,8 +638,13 @@ seq_kernel(const SeqParams p) {
                         decode16(v, carry_cf, carry_vm);
                         if (w0 == 1) carry_vm &= head_mask;
                     }
+                    // only a sequence that ends within 16 bytes of the end of the buffer needs the guarded load
+                    const uint4 *seq_chunks = reinterpret_cast<const uint4 *>(p.bases) + cbase;
+                    const bool near_end = ((cbase + nch) << 4) > p.total_bases;
                     auto fetch = [&](uint32_t c) -> uint4 {
-                        return (c < w1) ? load16_guarded(p.bases, (cbase + c) << 4, p.total_bases) : filler;
+                        if (c >= w1) return filler;
+                        if (near_end) return load16_guarded(p.bases, (cbase + c) << 4, p.total_bases);
+                        return __ldg(seq_chunks + c);
                     };
                     uint4 vnext = fetch(w0 + lane);
                     for (uint32_t c0 = w0; c0 < w1; c0 += 32) {
