@@ -7,6 +7,7 @@
 #include "textfmt.cuh"
 
 #include <charconv>
+#include <sys/stat.h>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -249,6 +250,14 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
     const size_t OUT_CAP = 256u << 20;
     const size_t max_records = std::max<size_t>(1, std::min<size_t>(OUT_CAP / out_per_row, 4u << 20));
     size_t bases_cap = 128u << 20;
+    {   // small inputs should not page-lock 128 MB per buffer set
+        struct stat sb;
+        if (in != "-" && stat(in.c_str(), &sb) == 0 && S_ISREG(sb.st_mode)) {
+            const bool gz = in.size() > 3 && in.compare(in.size() - 3, 3, ".gz") == 0;
+            const size_t est = (size_t)sb.st_size * (gz ? 8 : 1) + (1u << 20);
+            if (est < bases_cap) bases_cap = est;
+        }
+    }
 
     Set sets[2];
     for (auto &s : sets)
