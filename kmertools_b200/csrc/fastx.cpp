@@ -174,8 +174,37 @@ long FastxParser::fill(uint8_t *bases, size_t cap, size_t *used, std::vector<uin
 
     const uint8_t *lp;
     size_t ln;
+    // Sequence bytes go straight into the caller's buffer; only a record that does not fit is diverted to
+    // pending_ (and handed out first on the next call).
+    size_t rec_start = *used, w = *used;
+    bool overflow = false;
+    auto put = [&](const uint8_t *src, size_t t) {
+        if (!overflow && t <= cap - w) {
+            memcpy(bases + w, src, t);
+            w += t;
+            return;
+        }
+        if (!overflow) {
+            pending_.assign(bases + rec_start, bases + w);
+            overflow = true;
+        }
+        pending_.insert(pending_.end(), src, src + t);
+    };
+    auto commit = [&]() -> bool {   // false: the record is parked in pending_, stop this batch
+        if (overflow) {
+            in_record_ = true;
+            if (added == 0) need_ = pending_.size();
+            return false;
+        }
+        *used = w;
+        offsets->push_back(w);
+        ++added;
+        ++nrec_;
+        return true;
+    };
     while ((size_t)added < max_records) {
-        // ---- read one record into pending_ (sequence bytes only), then commit it
+        rec_start = w = *used;
+        overflow = false;
         if (fmt_ == SeqFormat::Fasta) {
             if (!have_header_) {
                 if (!next_line(&lp, &ln)) break;  // end of input
@@ -186,30 +215,24 @@ long FastxParser::fill(uint8_t *bases, size_t cap, size_t *used, std::vector<uin
                 }
                 have_header_ = true;
             }
-            pending_.clear();
             bool more = false;
             while (next_line(&lp, &ln)) {
                 if (ln > 0 && lp[0] == '>') { more = true; break; }
-                const size_t t = trim_end(lp, ln);
-                pending_.insert(pending_.end(), lp, lp + t);
+                put(lp, trim_end(lp, ln));
             }
             have_header_ = more;  // the '>' line just consumed opens the next record
-            in_record_ = true;
         } else {
             if (!next_line(&lp, &ln)) break;
-            if (ln == 0 && eof_ && pos_ == end_) break;
             if (ln == 0 || lp[0] != '@') {
                 if (trim_end(lp, ln) == 0) continue;
                 err_ = "Expected @ at record start.";
                 return -1;
             }
-            pending_.clear();
             size_t lines = 0;
             bool plus = false;
             while (next_line(&lp, &ln)) {
                 if (ln > 0 && lp[0] == '+') { plus = true; break; }
-                const size_t t = trim_end(lp, ln);
-                pending_.insert(pending_.end(), lp, lp + t);
+                put(lp, trim_end(lp, ln));
                 ++lines;
             }
             if (!plus) {
@@ -218,9 +241,8 @@ long FastxParser::fill(uint8_t *bases, size_t cap, size_t *used, std::vector<uin
             }
             for (size_t i = 0; i < lines; ++i)
                 if (!next_line(&lp, &ln)) break;  // quality lines are skipped
-            in_record_ = true;
         }
-        if (!flush_pending()) return added;
+        if (!commit()) return added;
     }
     return added;
 }
