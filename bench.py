@@ -193,7 +193,7 @@ def cpu_sample(spec: dict, bases_h: np.ndarray, offsets_h: np.ndarray, budget_re
     offs = np.ascontiguousarray(offsets_h[: n + 1]).astype(np.uint64)
     nb = int(offs[-1])
     thr = host_threads()
-    O.baseline_batch(bases_h[:nb], offs[: min(n, 1000) + 1], spec["k"], True, spec["norm"], thr)  # warm
+    O.baseline_batch(bases_h[:nb], offs, spec["k"], True, spec["norm"], thr)  # warm-up pass (allocator, page faults), as in --impl reference
     t0 = time.perf_counter()
     _, used = O.baseline_batch(bases_h[:nb], offs, spec["k"], True, spec["norm"], thr)
     dt = time.perf_counter() - t0
