@@ -66,10 +66,6 @@ typedef struct ktb_stats {
     uint64_t launches;     /* kernels launched by this library during the call */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
-    uint64_t n_short;      /* sequences handled by the thread-per-read kernel */
-    uint64_t n_medium;     /* sequences handled by the CTA-per-sequence shared-memory kernel */
-    uint64_t n_long;       /* sequences split into tiles */
-    uint64_t n_global;     /* sequences counted with global-memory atomics (large k) */
 } ktb_stats;
 
 /* Number of CUDA devices visible to the library (0 when there is none / no driver). */
@@ -119,9 +115,13 @@ int ktb_oligo_vectorise_device(ktb_oligo *h, const uint8_t *d_bases, const uint6
 int ktb_oligo_last_stats(const ktb_oligo *h, ktb_stats *out);
 
 /* Tuning knobs (testing / benchmarking).  Known keys:
- *   "chunk_bytes"   target bytes of output per pipeline chunk in the host entry point
- *   "force_path"    0 auto, 1 global-atomic path only, 2 no thread-per-read kernel
- *   "short_variant" 0 = byte read-modify-write histogram, 1 = packed shared-memory atomics */
+ *   "chunk_bytes"        target bytes of output per pipeline chunk in the host entry point
+ *   "force_path"         0 auto, 1 flat-decomposition global-atomic kernel only, 2 no short-read kernel
+ *   "seq_threads"        CTA size of the CTA-per-sequence kernel (0 = heuristic)
+ *   "dense_odd"          1 (default): dense middle-base histogram for k = 7, 0: code-space histogram
+ *   "packed16"           1: packed 16-bit code-space histogram for k = 8 (default 0: rank-space histogram)
+ *   "global_wave_bytes"  bytes of output rows zeroed + counted together in the global-atomic path (fits L2)
+ *   "short_warps", "short_variant"  accepted for compatibility with earlier revisions, no effect on results */
 int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value);
 
 /* Pinned host memory for callers that want asynchronous copies. */

@@ -26,8 +26,7 @@ class KtbError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("wall_ms", C.c_double), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64), ("n_short", C.c_uint64), ("n_medium", C.c_uint64),
-                ("n_long", C.c_uint64), ("n_global", C.c_uint64)]
+                ("d2h_bytes", C.c_uint64)]
 
 
 class FileOpts(C.Structure):
