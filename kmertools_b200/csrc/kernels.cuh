@@ -9,14 +9,19 @@
 //   row[rank(min(f,r))] += 1  (canonical)   |   row[f] += 1  (raw)          for every valid p
 //   row[j]   /= max(1, total)                      when normalising
 //
-// Three kernels cover the (length, k) plane:
-//   short_kernel  : one THREAD per read, byte-wide private histograms in shared memory (no atomics),
-//                   warp-transposed coalesced write-out.  Reads with <=255 windows, 4^k <= 1024.
-//   seq_kernel    : one CTA per sequence, 16 bases per lane per step from one 128-bit load, k-mers
-//                   cut out of a 2-bit packed 64-bit window, shared-memory atomics, fused
-//                   normalisation on write-out.  Any length, histogram fits shared memory.
-//   flat_kernel   : flat decomposition of the base stream, global-memory atomics into zeroed rows
-//                   (+ finalize_kernel).  Any k <= 12.
+// Kernels:
+//   short_kernel  : one WARP per group of 16 short reads (<= 255 windows each, 4^k <= 1024): read-aligned
+//                   16-base chunks per lane, byte counters packed four to a word, shared-memory atomics,
+//                   linear coalesced write-out with fused normalisation.  Groups it cannot take go to a
+//                   reject list.
+//   seq_kernel    : one CTA per sequence (consumes the reject list, or everything when k is large): warps walk
+//                   contiguous runs of 32-chunk steps with a carried look-back word; histogram in shared
+//                   memory in code space (mode 1), dense middle-base space (mode 4, k = 7), rank space
+//                   (mode 2, k = 8), packed 16-bit code space (mode 5, optional), raw (mode 0), or straight
+//                   into zeroed global rows with RED atomics for histograms larger than shared memory
+//                   (mode 3, driven in L2-sized waves by the host).
+//   finalize_kernel: u32 counts -> f32 / f64 rows for mode 3.
+//   flat_kernel   : flat decomposition of the base stream + global atomics; cross-check only (force_path=1).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
