@@ -260,10 +260,12 @@ __global__ void __launch_bounds__(256) short_kernel(const ShortParams p) {
         const uint32_t cpr_recip = uniform ? (0xFFFFFFFFu / cpr + 1u) : 0u;
 
         uint32_t carry_cf = 0, carry_vm = 0;
-        for (uint32_t t0 = 0; t0 < ntasks; t0 += 32) {
+        // one step = 32 chunk tasks; the loads of step s+1 are issued before step s is processed
+        struct Task { uint32_t r, q, a, nvalid; bool active; uint4 v0, v1; };
+        auto fetch_task = [&](uint32_t t0) -> Task {
+            Task tk;
             const uint32_t t = t0 + lane;
-            const bool active = t < ntasks;
-            // ---- which read / which chunk of it
+            tk.active = t < ntasks;
             uint32_t r, q;
             if (uniform) {
                 r = (cpr == 1) ? t : __umulhi(t, cpr_recip);
@@ -279,21 +281,32 @@ __global__ void __launch_bounds__(256) short_kernel(const ShortParams p) {
                 }
                 q = t - exr;
             }
-            r = active ? r : 0;
+            r = tk.active ? r : 0;
             const uint32_t rrel = __shfl_sync(FULL, rel, r);
             const uint32_t rlen = __shfl_sync(FULL, len, r);
-            uint32_t cf = (uint32_t)lane * 0x9E3779B1u, vm = 0;  // idle lanes add 0 at scattered bins
-            if (active) {
+            tk.r = r; tk.q = q; tk.a = 0; tk.nvalid = 0;
+            tk.v0 = tk.v1 = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+            if (tk.active) {
                 const uint64_t addr = gbase + rrel + 16u * q;
-                const uint32_t nvalid = min(16u, rlen - 16u * q);
-                const uint32_t a = (uint32_t)addr & 15u;
-                const uint64_t pa = addr - a;
-                const uint4 v0 = load16_guarded(p.bases, pa, p.total_bases);
-                uint4 u = v0;
-                if (a) {
-                    uint4 v1 = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-                    if (a + nvalid > 16u) v1 = load16_guarded(p.bases, pa + 16, p.total_bases);
-                    // byte funnel: u = bytes a..a+15 of (v0 : v1)
+                tk.nvalid = min(16u, rlen - 16u * q);
+                tk.a = (uint32_t)addr & 15u;
+                const uint64_t pa = addr - tk.a;
+                tk.v0 = load16_guarded(p.bases, pa, p.total_bases);
+                if (tk.a + tk.nvalid > 16u) tk.v1 = load16_guarded(p.bases, pa + 16, p.total_bases);
+            }
+            return tk;
+        };
+        Task cur = fetch_task(0);
+        for (uint32_t t0 = 0; t0 < ntasks; t0 += 32) {
+            Task nxt = cur;
+            if (t0 + 32 < ntasks) nxt = fetch_task(t0 + 32);
+            const uint32_t r = cur.r, q = cur.q;
+            uint32_t cf = (uint32_t)lane * 0x9E3779B1u, vm = 0;  // idle lanes add 0 at scattered bins
+            if (cur.active) {
+                const uint32_t a = cur.a;
+                uint4 u = cur.v0;
+                if (a) {   // byte funnel: u = bytes a..a+15 of (v0 : v1)
+                    const uint4 v0 = cur.v0, v1 = cur.v1;
                     uint32_t W0 = v0.x, W1 = v0.y, W2 = v0.z, W3 = v0.w, W4 = v1.x, W5 = v1.y, W6 = v1.z, W7 = v1.w;
                     if (a & 8u) { W0 = W2; W1 = W3; W2 = W4; W3 = W5; W4 = W6; W5 = W7; }
                     if (a & 4u) { W0 = W1; W1 = W2; W2 = W3; W3 = W4; W4 = W5; }
@@ -304,8 +317,9 @@ __global__ void __launch_bounds__(256) short_kernel(const ShortParams p) {
                     u.w = __funnelshift_r(W3, W4, bs);
                 }
                 decode16(u, cf, vm);
-                vm &= (0xFFFF0000u >> nvalid) & 0xFFFFu;   // bases past the end of the read
+                vm &= (0xFFFF0000u >> cur.nvalid) & 0xFFFFu;   // bases past the end of the read
             }
+            cur = nxt;
             uint32_t cf_prev = __shfl_up_sync(FULL, cf, 1);
             uint32_t vm_prev = __shfl_up_sync(FULL, vm, 1);
             if (lane == 0) { cf_prev = carry_cf; vm_prev = carry_vm; }
