@@ -186,6 +186,25 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank's host threads (and therefore its page-locked buffers, first touch) to the CPUs NVML
+    reports as local to the GPU, so 8 ranks do not push their D2H traffic across the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {w * 64 + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)[0], len(cpus)
+    except Exception:
+        return None
+    return None
+
+
 def cpu_sample(spec: dict, bases_h: np.ndarray, offsets_h: np.ndarray, budget_reads: int):
     """Time the oracle's port of the reference path on a bounded prefix of the workload."""
     from oracle import oracle as O
@@ -270,6 +289,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: kmertools_b200 has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -386,7 +406,7 @@ def main():
         e2e = {"value": world * total_bases / dt / 1e9, "unit": "Gbases/s",
                "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]),
                "ms_per_step": dt * 1e3, "kernel_ms": st["kernel_ms"], "h2d_ms": st["h2d_ms"], "d2h_ms": st["d2h_ms"],
-               "host_memory": host_kind}
+               "host_memory": host_kind, "numa_binding": numa}
         # parity spot check against the device-path result
         same = bool(np.array_equal(hout.array[:1000], out[:1000].cpu().numpy()))
         e2e["matches_device_path"] = same
@@ -398,6 +418,10 @@ def main():
     # ---- CPU baseline on rank 0 (bounded sample)
     cpu = None
     if rank == 0 and not args.no_cpu:
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))   # the CPU arm uses every host core
+        except Exception:
+            pass
         if keep_h is not None:
             bh, oh = keep_h[0].array, keep_h[1].array
         else:
