@@ -367,8 +367,15 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     B = algorithmic_bytes(total_bases, n, dim, esize)
     achieved = B / (ms_per_step * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tpath = ROOT / "profiles" / "ncu_dram_traffic.json"   # dram__bytes_read+write of the dominant kernel (one ncu --set full capture)
+    if tpath.exists():
+        ent = json.loads(tpath.read_text()).get(args.workload)
+        if ent:
+            traffic = ent["dram_bytes_per_sequence"] * n
+            traffic_src = f"{ent['kernel']}: {ent['capture']}, scaled per sequence ({ent['summary']})"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": B,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_step": B,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
     # ---- e2e through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)
