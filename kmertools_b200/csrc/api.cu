@@ -118,6 +118,7 @@ struct ktb_oligo {
     int seq_threads = 0;  // 0 = auto (256)
     int dense_odd = 1;    // use seq_kernel mode 4 where it applies
     int packed16 = 0;     // seq_kernel mode 5 (k = 8 packed code space): measured no faster than mode 2, off by default
+    int global_steps_per_warp = 1;
     int64_t global_wave_bytes = 64ll << 20;  // rows zeroed + counted together in the global-atomic path (fits L2)
     ktb_stats stats{};
 };
@@ -352,9 +353,12 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         const uint64_t wave = std::max<uint64_t>(1, std::min<uint64_t>(n, (uint64_t)h->global_wave_bytes / 2 / row_bytes));
         if (OUT == OUT_F64)
             if (int rc = h->ws_counts.ensure(2 * wave * row_bytes)) return rc;
-        // a work item = (sequence, tile); aim at ~4 steps of 512 bases per warp
+        // a work item = (sequence, tile).  A wave is small (rows must fit L2), so parallelism has to come from
+        // splitting sequences finely: about `global_steps_per_warp` steps of 512 bases per warp (the first
+        // version used 4 and ran 5 warps per SM; one step per warp fills the machine).
         const uint64_t mean_steps = (total_bases / std::max<uint64_t>(n, 1)) / 512 + 1;
-        const uint32_t tiles = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(256, mean_steps / (4 * (threads / 32))));
+        const uint64_t per_item = (uint64_t)std::max(1, h->global_steps_per_warp) * (threads / 32);
+        const uint32_t tiles = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(4096, mean_steps / per_item));
         CU(cudaEventRecord(h->aux_ev[2], st));
         uint64_t w = 0;
         for (uint64_t i0 = 0; i0 < n; i0 += wave, ++w) {
@@ -663,6 +667,8 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->packed16 = (int)value;
     } else if (!strcmp(key, "dense_odd")) {
         h->dense_odd = (int)value;
+    } else if (!strcmp(key, "global_steps_per_warp")) {
+        h->global_steps_per_warp = (int)value;
     } else if (!strcmp(key, "global_wave_bytes")) {
         if (value < 1) return fail(KTB_ERR_ARG, "global_wave_bytes must be positive");
         h->global_wave_bytes = value;
