@@ -271,6 +271,7 @@ def main():
     ap.add_argument("--seq-threads", type=int, default=None)
     ap.add_argument("--global-wave-mb", type=int, default=None)
     ap.add_argument("--dense-odd", type=int, default=None)
+    ap.add_argument("--even-rank", type=int, default=None)
     ap.add_argument("--global-steps-per-warp", type=int, default=None)
     args = ap.parse_args()
     spec = WORKLOADS[args.workload]
@@ -306,6 +307,8 @@ def main():
         oc.set_option("seq_threads", args.seq_threads)
     if args.global_steps_per_warp is not None:
         oc.set_option("global_steps_per_warp", args.global_steps_per_warp)
+    if args.even_rank is not None:
+        oc.set_option("even_rank", args.even_rank)
     if args.dense_odd is not None:
         oc.set_option("dense_odd", args.dense_odd)
     if args.global_wave_mb is not None:

@@ -98,6 +98,8 @@ struct ktb_oligo {
     uint32_t *d_canon_perm = nullptr;      // canon_of_rank permuted inside 128-rank blocks (seq_kernel gather)
     uint32_t *d_mb_of_rank = nullptr;      // odd k: rank -> dense middle-base index (seq_kernel mode 4)
     uint32_t *d_mb_perm = nullptr;
+    uint32_t *d_even_tab = nullptr;        // even k: bitmap words + u16 prefixes for the in-kernel rank (mode 7)
+    uint32_t even_words = 0;
     uint32_t *d_pk_of_rank = nullptr;      // mode 5: rank -> (16*half) << 24 | byte offset of the packed word
     uint32_t *d_pk_perm = nullptr;
     uint64_t mb_entries = 0;               // histogram words mode 4 needs (dense index + skew)
@@ -117,6 +119,7 @@ struct ktb_oligo {
     int short_warps = 0;  // 0 = auto
     int seq_threads = 0;  // 0 = auto (256)
     int dense_odd = 1;    // use seq_kernel mode 4 where it applies
+    int even_rank = 1;    // use seq_kernel mode 7 where it applies
     int packed16 = 0;     // seq_kernel mode 5 (k = 8 packed code space): measured no faster than mode 2, off by default
     int global_steps_per_warp = 1;
     int64_t global_wave_bytes = 64ll << 20;  // rows zeroed + counted together in the global-atomic path (fits L2)
@@ -176,13 +179,15 @@ int launch_short(ktb_oligo *h, const ShortParams &p, const ShortCfg &c, cudaStre
 
 template <int OUT>
 int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st) {
-    const size_t smem = (size_t)p.hist_entries * 4;
+    const size_t smem = (hist_mode == 7) ? ((((size_t)p.hist_entries + 3) & ~(size_t)3) * 4 + (size_t)p.even_words * 6 + 16)
+                                         : (size_t)p.hist_entries * 4;
     void (*kern)(const SeqParams) = nullptr;
     const bool nrm = p.norm_mode != NORM_COUNTS;
     if (hist_mode == 0) kern = nrm ? seq_kernel<OUT, 0, true> : seq_kernel<OUT, 0, false>;
     else if (hist_mode == 1) kern = nrm ? seq_kernel<OUT, 1, true> : seq_kernel<OUT, 1, false>;
     else if (hist_mode == 4) kern = nrm ? seq_kernel<OUT, 4, true> : seq_kernel<OUT, 4, false>;
     else if (hist_mode == 5) kern = nrm ? seq_kernel<OUT, 5, true> : seq_kernel<OUT, 5, false>;
+    else if (hist_mode == 7) kern = nrm ? seq_kernel<OUT, 7, true> : seq_kernel<OUT, 7, false>;
     else kern = nrm ? seq_kernel<OUT, 2, true> : seq_kernel<OUT, 2, false>;
     if constexpr (OUT == OUT_F32) {
         if (hist_mode == 4 && nrm && p.k == 7) kern = seq_kernel<OUT_F32, 4, true, 7>;   // k folded into immediates for the headline shapes
@@ -204,7 +209,7 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
     const int auto_threads = (hist_mode == 5) ? 1024 : ((mean_len <= 16384 && smem <= 16 * 1024) ? 128 : 256);
     int threads = h->seq_threads > 0 ? h->seq_threads : auto_threads;
-    if (hist_mode != 2 && hist_mode != 5 && threads > KTB_SEQ_MAXTHREADS) threads = KTB_SEQ_MAXTHREADS;
+    if (hist_mode != 2 && hist_mode != 5 && hist_mode != 7 && threads > KTB_SEQ_MAXTHREADS) threads = KTB_SEQ_MAXTHREADS;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)h->sm_count * per_sm;
@@ -238,6 +243,8 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
             hist_mode = 1; hist_entries = h->ncodes;
         } else if (h->d_pk_perm && h->packed16) {
             hist_mode = 5; hist_entries = h->ncodes / 2;   // k = 8: packed 16-bit code space, 128 KB
+        } else if (h->d_even_tab && h->even_rank && h->dim_canon * 4 + h->even_words * 6 + 64 <= smem_limit) {
+            hist_mode = 7; hist_entries = h->dim_canon;      // k = 8: rank from shared-memory bitmap tables
         } else if (h->dim_canon * 4 <= smem_limit) {
             hist_mode = 2; hist_entries = h->dim_canon;
         }
@@ -275,6 +282,7 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         qp.list = sc.ok ? (const uint32_t *)h->ws_list.p : nullptr;
         qp.list_count = sc.ok ? h->d_counters + 2 : nullptr;
         qp.group_size = SHORT_G;
+        qp.even_tab = h->d_even_tab; qp.even_words = h->even_words;
         if (hist_mode == 5) {
             // packed 16-bit counters: sequences with more than 65535 windows come back on out_list and are
             // redone by the rank-space kernel (mode 2) in a second launch
@@ -537,6 +545,27 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
             CUB(cudaMalloc(&h->d_pk_perm, pkp.size() * 4));
             CUB(cudaMemcpy(h->d_pk_perm, pkp.data(), pkp.size() * 4, cudaMemcpyHostToDevice));
         }
+        if (!(k & 1) && k >= 6 && k <= 8) {  // rank tables of seq_kernel mode 7 (see kernels.cuh)
+            const uint32_t hd = k / 2, H = 1u << (2 * hd), wpr = H / 32;   // halves of hd bases, words per row
+            std::vector<uint32_t> tab((size_t)H * wpr + ((size_t)H * wpr + 1) / 2, 0);
+            uint16_t *pref = reinterpret_cast<uint16_t *>(tab.data() + (size_t)H * wpr);
+            uint32_t running = 0;
+            for (uint32_t a = 0; a < H; ++a) {
+                for (uint32_t w = 0; w < wpr; ++w) {
+                    uint32_t bits = 0;
+                    for (uint32_t i = 0; i < 32; ++i)
+                        if ((uint32_t)rev_comp(32 * w + i, hd) >= a) bits |= 1u << i;   // (a, R) canonical <=> a <= rc(R)
+                    tab[(size_t)a * wpr + w] = bits;
+                    pref[(size_t)a * wpr + w] = (uint16_t)running;
+                    running += (uint32_t)__builtin_popcount(bits);
+                }
+            }
+            if (running == h->dim_canon && h->dim_canon <= 65535u + 32u) {
+                h->even_words = H * wpr;
+                CUB(cudaMalloc(&h->d_even_tab, tab.size() * 4));
+                CUB(cudaMemcpy(h->d_even_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+            }
+        }
         if (k & 1) {  // dense half-size index of seq_kernel mode 4 (see kernels.cuh)
             const uint32_t midbit = 1u << (2 * (k / 2) + 1);
             std::vector<uint32_t> mb(cor.size(), 0), mbp(cor.size(), 0);
@@ -611,6 +640,7 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     if (h->d_canon_perm) cudaFree(h->d_canon_perm);
     if (h->d_mb_of_rank) cudaFree(h->d_mb_of_rank);
     if (h->d_mb_perm) cudaFree(h->d_mb_perm);
+    if (h->d_even_tab) cudaFree(h->d_even_tab);
     if (h->d_pk_of_rank) cudaFree(h->d_pk_of_rank);
     if (h->d_pk_perm) cudaFree(h->d_pk_perm);
     if (h->d_short_tab_canon) cudaFree(h->d_short_tab_canon);
@@ -665,6 +695,8 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->short_warps = (int)value;
     } else if (!strcmp(key, "packed16")) {
         h->packed16 = (int)value;
+    } else if (!strcmp(key, "even_rank")) {
+        h->even_rank = (int)value;
     } else if (!strcmp(key, "dense_odd")) {
         h->dense_odd = (int)value;
     } else if (!strcmp(key, "global_steps_per_warp")) {

@@ -430,10 +430,17 @@ struct SeqParams {
     uint64_t seq_base;           // HIST_MODE 3: first sequence of this wave
     uint64_t seq_count;          // HIST_MODE 3: sequences in this wave
     uint32_t tiles;              // HIST_MODE 3: CTAs cooperating on one sequence (work item = sequence x tile)
+    const uint32_t *even_tab;    // HIST_MODE 7: [H*(H/32)] bitmap words then [H*(H/32)] u16 prefixes (see api.cu)
+    uint32_t even_words;         // HIST_MODE 7: H*(H/32)
     uint32_t *out_list;          // HIST_MODE 5: sequences with > 65535 windows are appended here (next launch)
     unsigned long long *out_count;
 };
 
+// HIST_MODE 7 = rank space for EVEN k with the rank computed from two small shared-memory tables instead of a
+//             4^k-entry table in L2 (mode 2 spends ~600 cycles of latency per k-mer on that look-up with only 8
+//             warps per SM).  Write the code as (a, R), two halves of k/2 bases; it is canonical iff
+//             a <= rc(R), so rank(a, R) = prefix[a][R/32] + popc(bitmap[a][R/32] & ((1 << R%32) - 1)) where
+//             bitmap[a] marks the R' with rc(R') >= a.  k = 8: 8 KB + 4 KB of tables.
 // HIST_MODE 5 = code space with 16-bit counters packed two to a word (k = 8: 4^8 codes in 128 KB, no rank
 //             table look-ups at all; k = 8 canonical in rank space needed one random L2 access per k-mer and
 //             ran at one look-up per cycle per SM).  Code c lives in word c & (H-1), half c >> log2(H).
@@ -571,8 +578,8 @@ __device__ __forceinline__ void seq_write_row(uint32_t *hist, typename OutT<OUT>
 // KT: compile-time k (0 = use p.k); the specialised instances fold the window-mask loop and every
 // shift amount into immediates.
 template <int OUT, int HIST_MODE, bool NORM, int KT = 0>
-__global__ void __launch_bounds__((HIST_MODE == 2 || HIST_MODE == 5) ? 1024 : KTB_SEQ_MAXTHREADS,
-                                  (HIST_MODE == 2 || HIST_MODE == 5) ? 1 : ((HIST_MODE == 4) ? KTB_SEQ_MINBLOCKS4 : KTB_SEQ_MINBLOCKS))
+__global__ void __launch_bounds__((HIST_MODE == 2 || HIST_MODE == 5 || HIST_MODE == 7) ? 1024 : KTB_SEQ_MAXTHREADS,
+                                  (HIST_MODE == 2 || HIST_MODE == 5 || HIST_MODE == 7) ? 1 : ((HIST_MODE == 4) ? KTB_SEQ_MINBLOCKS4 : KTB_SEQ_MINBLOCKS))
 seq_kernel(const SeqParams p) {
     extern __shared__ __align__(16) uint32_t hist[];
     __shared__ unsigned long long s_group;
@@ -588,6 +595,15 @@ seq_kernel(const SeqParams p) {
                             : (p.list ? (uint64_t)*p.list_count : (p.n + p.group_size - 1) / p.group_size) * p.group_size;
     if ((uint64_t)blockIdx.x >= nitems) return;  // nothing for this CTA (e.g. short_kernel took everything)
     for (uint32_t i = tid; i < p.hist_entries; i += blockDim.x) hist[i] = 0;
+    // mode 7: rank tables behind the histogram (bitmap words, then u16 prefixes)
+    uint32_t *s_bitmap = hist + ((p.hist_entries + 3u) & ~3u);
+    uint16_t *s_prefix = reinterpret_cast<uint16_t *>(s_bitmap + p.even_words);
+    if constexpr (HIST_MODE == 7) {
+        for (uint32_t i = tid; i < p.even_words; i += blockDim.x) s_bitmap[i] = __ldg(p.even_tab + i);
+        const uint16_t *gp = reinterpret_cast<const uint16_t *>(p.even_tab + p.even_words);
+        for (uint32_t i = tid; i < p.even_words; i += blockDim.x) s_prefix[i] = gp[i];
+    }
+    (void)s_bitmap; (void)s_prefix;
     if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
     __syncthreads();
     uint32_t it = 0;
@@ -685,7 +701,7 @@ seq_kernel(const SeqParams p) {
                         mine += __popc(vw);
                         const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
                         uint64_t R64 = 0;
-                        if constexpr (HIST_MODE == 1 || HIST_MODE == 4 || HIST_MODE == 5) {
+                        if constexpr (HIST_MODE == 1 || HIST_MODE == 4 || HIST_MODE == 5 || HIST_MODE == 7) {
                             R64 = ((uint64_t)revcomp_pack(cf) << 32) | revcomp_pack(cf_prev);
                         }
                         uint32_t idx4[16];  // histogram byte offsets
@@ -708,6 +724,12 @@ seq_kernel(const SeqParams p) {
                             } else if constexpr (HIST_MODE == 5) {
                                 const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
                                 idx4[j] = p.canonical ? min(f4, r4) : f4;   // unpacked below
+                            } else if constexpr (HIST_MODE == 7) {
+                                const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
+                                const uint32_t c = min(f4, r4) >> 2;                 // canonical code (a, R)
+                                const uint32_t w = c >> 5;                           // a * (H/32) + R / 32
+                                const uint32_t below = s_bitmap[w] & ((1u << (c & 31u)) - 1u);
+                                idx4[j] = ((uint32_t)s_prefix[w] + (uint32_t)__popc(below)) << 2;
                             } else if constexpr (HIST_MODE == 2) {
                                 idx4[j] = __ldg(p.rank_full + (f4 >> 2)) << 2;
                             } else {

@@ -23,16 +23,16 @@ def comp(k):
 
 def check(k, bases, offsets, mins=True, norm_mode=NORM_CLI, dtype=np.float32, what="", **opts):
     oc = comp(k)
-    for key in ("force_path", "short_variant", "packed16"):
-        oc.set_option(key, opts.get(key, 0))
+    for key, dflt in (("force_path", 0), ("short_variant", 0), ("packed16", 0), ("even_rank", 1), ("dense_odd", 1)):
+        oc.set_option(key, opts.get(key, dflt))
     n = len(offsets) - 1
     totals = np.zeros(n, dtype=np.uint64)
     got = oc.vectorise_packed(bases, offsets, norm_mode=norm_mode, mins=mins, dtype=dtype, totals=totals)
     want, wtot = O.vectorise_batch(bases, offsets, k, mins, norm_mode)
     assert np.array_equal(totals, wtot), f"{what}: totals differ"
     assert_rows_equal(got, want, dtype, what)
-    for key in ("force_path", "short_variant", "packed16"):
-        oc.set_option(key, 0)
+    for key, dflt in (("force_path", 0), ("short_variant", 0), ("packed16", 0), ("even_rank", 1), ("dense_odd", 1)):
+        oc.set_option(key, dflt)
     return got
 
 
@@ -160,6 +160,18 @@ def test_k8_packed16_variant_with_overflow_fallback():
     check(8, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, packed16=1, what="k8 packed counts")
     check(8, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, packed16=1, what="k8 packed f32")
     check(8, bases, offsets, norm_mode=NORM_CLI, dtype=np.float64, packed16=1, what="k8 packed f64")
+
+
+def test_alternative_histogram_modes_agree():
+    """The non-default histogram layouts stay correct: k=8 through the L2 rank table (mode 2) and k=7 through the
+    code-space histogram (mode 1) instead of the in-kernel rank (mode 7) / dense middle-base index (mode 4)."""
+    rng = np.random.default_rng(66)
+    lengths = np.r_[rng.integers(0, 6000, size=60), [40000, 90000]]
+    bases, offsets = random_batch(rng, lengths, noise=0.002, n_runs=0.3)
+    check(8, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, even_rank=0, what="k8 mode 2")
+    check(8, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, even_rank=0, what="k8 mode 2 f32")
+    check(7, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, dense_odd=0, what="k7 mode 1")
+    check(7, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, dense_odd=0, what="k7 mode 1 f32")
 
 
 @pytest.mark.parametrize("k", [9, 10])
