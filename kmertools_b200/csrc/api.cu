@@ -100,8 +100,6 @@ struct ktb_oligo {
     uint32_t *d_mb_perm = nullptr;
     uint32_t *d_even_tab = nullptr;        // even k: bitmap words + u16 prefixes for the in-kernel rank (mode 7)
     uint32_t even_words = 0;
-    uint32_t *d_pk_of_rank = nullptr;      // mode 5: rank -> (16*half) << 24 | byte offset of the packed word
-    uint32_t *d_pk_perm = nullptr;
     uint64_t mb_entries = 0;               // histogram words mode 4 needs (dense index + skew)
     uint32_t *d_short_tab_canon = nullptr; // [4^k] (k <= 5): (word byte offset << 22) | 8*(bin&3)
     uint32_t *d_short_tab_raw = nullptr;
@@ -120,7 +118,7 @@ struct ktb_oligo {
     int seq_threads = 0;  // 0 = auto (256)
     int dense_odd = 1;    // use seq_kernel mode 4 where it applies
     int even_rank = 1;    // use seq_kernel mode 7 where it applies
-    int packed16 = 0;     // seq_kernel mode 5 (k = 8 packed code space): measured no faster than mode 2, off by default
+    int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
     int global_steps_per_warp = 1;
     int64_t global_wave_bytes = 64ll << 20;  // rows zeroed + counted together in the global-atomic path (fits L2)
     ktb_stats stats{};
@@ -179,7 +177,7 @@ int launch_short(ktb_oligo *h, const ShortParams &p, const ShortCfg &c, cudaStre
 
 template <int OUT>
 int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st) {
-    const size_t smem = (hist_mode == 7) ? ((((size_t)p.hist_entries + 3) & ~(size_t)3) * 4 + (size_t)p.even_words * 6 + 16)
+    const size_t smem = (hist_mode == 7 || hist_mode == 5) ? ((((size_t)p.hist_entries + 3) & ~(size_t)3) * 4 + (size_t)p.even_words * 6 + 16)
                                          : (size_t)p.hist_entries * 4;
     void (*kern)(const SeqParams) = nullptr;
     const bool nrm = p.norm_mode != NORM_COUNTS;
@@ -207,8 +205,9 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     // per CTA (less barrier / priming overhead, occupancy is not the limit); long contigs and the big
     // histograms want 8 warps.
     const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
-    const int auto_threads = (hist_mode == 5) ? 1024 : ((mean_len <= 16384 && smem <= 16 * 1024) ? 128 : 256);
+    const int auto_threads = ((mean_len <= 16384 && smem <= 16 * 1024) ? 128 : 256);
     int threads = h->seq_threads > 0 ? h->seq_threads : auto_threads;
+    if (hist_mode == 5 && threads > 512) threads = 512;
     if (hist_mode != 2 && hist_mode != 5 && hist_mode != 7 && threads > KTB_SEQ_MAXTHREADS) threads = KTB_SEQ_MAXTHREADS;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
@@ -241,8 +240,9 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
             hist_mode = 4; hist_entries = (h->mb_entries + 3) & ~3ull;   // k = 7: dense middle-base index, 32 KB + skew
         } else if (h->ncodes * 4 <= 64 * 1024) {
             hist_mode = 1; hist_entries = h->ncodes;
-        } else if (h->d_pk_perm && h->packed16) {
-            hist_mode = 5; hist_entries = h->ncodes / 2;   // k = 8: packed 16-bit code space, 128 KB
+        } else if (h->d_even_tab && h->even_rank && h->packed16 && (h->dim_canon % 8) == 0 &&
+                   h->dim_canon * 2 + h->even_words * 6 + 64 <= smem_limit / 2) {
+            hist_mode = 5; hist_entries = h->dim_canon / 2;   // k = 8: packed 16-bit rank space, 2 CTAs/SM
         } else if (h->d_even_tab && h->even_rank && h->dim_canon * 4 + h->even_words * 6 + 64 <= smem_limit) {
             hist_mode = 7; hist_entries = h->dim_canon;      // k = 8: rank from shared-memory bitmap tables
         } else if (h->dim_canon * 4 <= smem_limit) {
@@ -285,17 +285,15 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         qp.even_tab = h->d_even_tab; qp.even_words = h->even_words;
         if (hist_mode == 5) {
             // packed 16-bit counters: sequences with more than 65535 windows come back on out_list and are
-            // redone by the rank-space kernel (mode 2) in a second launch
+            // redone with 32-bit counters (mode 7) in a second launch
             if (int rc = h->ws_list2.ensure(n * 4)) return rc;
-            qp.canon_of_rank = h->d_pk_of_rank; qp.canon_perm = h->d_pk_perm;
             qp.out_list = (uint32_t *)h->ws_list2.p; qp.out_count = h->d_counters + 3;
             if (int rc = launch_seq<OUT>(h, qp, 5, st)) return rc;
             SeqParams q2 = qp;
-            q2.canon_of_rank = h->d_canon_of_rank; q2.canon_perm = h->d_canon_perm;
             q2.hist_entries = (uint32_t)h->dim_canon;
             q2.counter = h->d_counters + 0;   // unused by the short kernel for this k, zeroed above
             q2.list = (const uint32_t *)h->ws_list2.p; q2.list_count = h->d_counters + 3; q2.group_size = 1;
-            return launch_seq<OUT>(h, q2, 2, st);
+            return launch_seq<OUT>(h, q2, 7, st);
         }
         return launch_seq<OUT>(h, qp, hist_mode, st);
     }
@@ -532,19 +530,6 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
                 for (uint32_t e = 0; e < 4; ++e) perm[b * 128 + 4 * l + e] = cor[b * 128 + 32 * e + l];
         CUB(cudaMalloc(&h->d_canon_perm, perm.size() * 4));
         CUB(cudaMemcpy(h->d_canon_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
-        if (h->ncodes * 4 > 200 * 1024 && h->ncodes * 2 <= 200 * 1024) {  // packed 16-bit code space (mode 5): k = 8
-            const uint64_t H = h->ncodes / 2;
-            std::vector<uint32_t> pk(cor.size(), 0), pkp(cor.size(), 0);
-            for (uint64_t j = 0; j < h->dim_canon; ++j)
-                pk[j] = (uint32_t)(((cor[j] >= H ? 16u : 0u) << 24) | ((cor[j] & (H - 1)) * 4));
-            for (uint64_t b = 0; b < nblk; ++b)
-                for (uint32_t l = 0; l < 32; ++l)
-                    for (uint32_t e = 0; e < 4; ++e) pkp[b * 128 + 4 * l + e] = pk[b * 128 + 32 * e + l];
-            CUB(cudaMalloc(&h->d_pk_of_rank, pk.size() * 4));
-            CUB(cudaMemcpy(h->d_pk_of_rank, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
-            CUB(cudaMalloc(&h->d_pk_perm, pkp.size() * 4));
-            CUB(cudaMemcpy(h->d_pk_perm, pkp.data(), pkp.size() * 4, cudaMemcpyHostToDevice));
-        }
         if (!(k & 1) && k >= 6 && k <= 8) {  // rank tables of seq_kernel mode 7 (see kernels.cuh)
             const uint32_t hd = k / 2, H = 1u << (2 * hd), wpr = H / 32;   // halves of hd bases, words per row
             std::vector<uint32_t> tab((size_t)H * wpr + ((size_t)H * wpr + 1) / 2, 0);
@@ -641,8 +626,6 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     if (h->d_mb_of_rank) cudaFree(h->d_mb_of_rank);
     if (h->d_mb_perm) cudaFree(h->d_mb_perm);
     if (h->d_even_tab) cudaFree(h->d_even_tab);
-    if (h->d_pk_of_rank) cudaFree(h->d_pk_of_rank);
-    if (h->d_pk_perm) cudaFree(h->d_pk_perm);
     if (h->d_short_tab_canon) cudaFree(h->d_short_tab_canon);
     if (h->d_short_tab_raw) cudaFree(h->d_short_tab_raw);
     if (h->d_counters) cudaFree(h->d_counters);

@@ -441,10 +441,10 @@ struct SeqParams {
 //             warps per SM).  Write the code as (a, R), two halves of k/2 bases; it is canonical iff
 //             a <= rc(R), so rank(a, R) = prefix[a][R/32] + popc(bitmap[a][R/32] & ((1 << R%32) - 1)) where
 //             bitmap[a] marks the R' with rc(R') >= a.  k = 8: 8 KB + 4 KB of tables.
-// HIST_MODE 5 = code space with 16-bit counters packed two to a word (k = 8: 4^8 codes in 128 KB, no rank
-//             table look-ups at all; k = 8 canonical in rank space needed one random L2 access per k-mer and
-//             ran at one look-up per cycle per SM).  Code c lives in word c & (H-1), half c >> log2(H).
-//             Sequences with more than 65535 windows are passed on to the next launch (out_list).
+// HIST_MODE 5 = mode 7's in-kernel rank + 16-bit counters packed two to a word (rank r -> word r/2, half r&1):
+//             k = 8 needs 64.25 KB + 12 KB instead of 128.5 KB + 12 KB, so two CTAs per SM can overlap their
+//             accumulate and write-out phases.  Sequences with more than 65535 windows are passed on to a
+//             second launch of mode 7 (out_list).
 // HIST_MODE 4 = canonical, ODD k, dense half-size histogram: the two strands of an odd k-mer differ in the
 //             top bit of their MIDDLE base (m vs 3-m), so "the strand whose middle base is A or C" is a
 //             table-free representative; dropping that bit gives a dense index in [0, 4^k/2).  Half the
@@ -485,28 +485,30 @@ __device__ __forceinline__ void seq_write_row(uint32_t *hist, typename OutT<OUT>
     // monotone codes fall into distinct banks — fetched with ONE 128-bit load from a table permuted on
     // the host, and written back with four fully coalesced 32-bit stores.
     if constexpr (HIST_MODE == 5) {
-        // packed 16-bit counters: canon_perm entries are (16 * half) << 24 | byte offset of the word; gather
-        // (lanes take consecutive ranks), convert, store; the histogram is zeroed in bulk afterwards because
-        // two codes share a word.
-        const uint32_t nblk = p.dim >> 7;
-        const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-        const uint8_t *hb = reinterpret_cast<const uint8_t *>(hist);
-        auto cnt_of = [&](uint32_t e) -> uint32_t {
-            return (*reinterpret_cast<const uint32_t *>(hb + (e & 0xFFFFFFu)) >> (e >> 24)) & 0xFFFFu;
-        };
-        for (uint32_t b = warp; b < nblk; b += nwarps) {
-            const uint4 cc = __ldg(reinterpret_cast<const uint4 *>(p.canon_perm + (b << 7)) + lane);
-            T *dst = row + (b << 7) + lane;
-            dst[0] = cvt_count<OUT, NORM, SMALL>(cnt_of(cc.x), dF, rinv, dD);
-            dst[32] = cvt_count<OUT, NORM, SMALL>(cnt_of(cc.y), dF, rinv, dD);
-            dst[64] = cvt_count<OUT, NORM, SMALL>(cnt_of(cc.z), dF, rinv, dD);
-            dst[96] = cvt_count<OUT, NORM, SMALL>(cnt_of(cc.w), dF, rinv, dD);
+        // rank space, 16-bit counters packed two to a word (rank r -> word r/2, half r&1): linear sweep, one
+        // 128-bit shared load = 8 counts = two 128-bit (f32/u32) stores; zeroed on the way.  dim % 8 == 0.
+        for (uint32_t w = tid * 4u; w < p.hist_entries; w += blockDim.x * 4u) {
+            const uint4 hv = *reinterpret_cast<const uint4 *>(hist + w);
+            *reinterpret_cast<uint4 *>(hist + w) = make_uint4(0, 0, 0, 0);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+            T e[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                e[2 * q] = cvt_count<OUT, NORM, SMALL>(hw[q] & 0xFFFFu, dF, rinv, dD);
+                e[2 * q + 1] = cvt_count<OUT, NORM, SMALL>(hw[q] >> 16, dF, rinv, dD);
+            }
+            T *dst = row + 2u * w;
+            if constexpr (OUT == OUT_F64) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) reinterpret_cast<double2 *>(dst)[q] = make_double2(e[2 * q], e[2 * q + 1]);
+            } else if constexpr (OUT == OUT_F32) {
+                reinterpret_cast<float4 *>(dst)[0] = make_float4(e[0], e[1], e[2], e[3]);
+                reinterpret_cast<float4 *>(dst)[1] = make_float4(e[4], e[5], e[6], e[7]);
+            } else {
+                reinterpret_cast<uint4 *>(dst)[0] = make_uint4(e[0], e[1], e[2], e[3]);
+                reinterpret_cast<uint4 *>(dst)[1] = make_uint4(e[4], e[5], e[6], e[7]);
+            }
         }
-        for (uint32_t j = (nblk << 7) + tid; j < p.dim; j += blockDim.x)
-            row[j] = cvt_count<OUT, NORM, SMALL>(cnt_of(__ldg(p.canon_of_rank + j)), dF, rinv, dD);
-        __syncthreads();
-        uint4 *hz = reinterpret_cast<uint4 *>(hist);
-        for (uint32_t i = tid; i < p.hist_entries / 4; i += blockDim.x) hz[i] = make_uint4(0, 0, 0, 0);
         return;
     }
     if constexpr (HIST_MODE == 1 || HIST_MODE == 4) {
@@ -578,8 +580,8 @@ __device__ __forceinline__ void seq_write_row(uint32_t *hist, typename OutT<OUT>
 // KT: compile-time k (0 = use p.k); the specialised instances fold the window-mask loop and every
 // shift amount into immediates.
 template <int OUT, int HIST_MODE, bool NORM, int KT = 0>
-__global__ void __launch_bounds__((HIST_MODE == 2 || HIST_MODE == 5 || HIST_MODE == 7) ? 1024 : KTB_SEQ_MAXTHREADS,
-                                  (HIST_MODE == 2 || HIST_MODE == 5 || HIST_MODE == 7) ? 1 : ((HIST_MODE == 4) ? KTB_SEQ_MINBLOCKS4 : KTB_SEQ_MINBLOCKS))
+__global__ void __launch_bounds__((HIST_MODE == 2 || HIST_MODE == 7) ? 1024 : ((HIST_MODE == 5) ? 512 : KTB_SEQ_MAXTHREADS),
+                                  (HIST_MODE == 2 || HIST_MODE == 7) ? 1 : (HIST_MODE == 5) ? 2 : ((HIST_MODE == 4) ? KTB_SEQ_MINBLOCKS4 : KTB_SEQ_MINBLOCKS))
 seq_kernel(const SeqParams p) {
     extern __shared__ __align__(16) uint32_t hist[];
     __shared__ unsigned long long s_group;
@@ -598,7 +600,7 @@ seq_kernel(const SeqParams p) {
     // mode 7: rank tables behind the histogram (bitmap words, then u16 prefixes)
     uint32_t *s_bitmap = hist + ((p.hist_entries + 3u) & ~3u);
     uint16_t *s_prefix = reinterpret_cast<uint16_t *>(s_bitmap + p.even_words);
-    if constexpr (HIST_MODE == 7) {
+    if constexpr (HIST_MODE == 7 || HIST_MODE == 5) {
         for (uint32_t i = tid; i < p.even_words; i += blockDim.x) s_bitmap[i] = __ldg(p.even_tab + i);
         const uint16_t *gp = reinterpret_cast<const uint16_t *>(p.even_tab + p.even_words);
         for (uint32_t i = tid; i < p.even_words; i += blockDim.x) s_prefix[i] = gp[i];
@@ -614,9 +616,6 @@ seq_kernel(const SeqParams p) {
     const uint32_t mb_shift = 2 * (k / 2) + 4;              // s4 >> mb_shift = digits above the middle bit
     const uint32_t mb_mul = midbit4 - 4u * (midbit4 >> 9);  // 2^m*4 minus the skew of 4 bytes per 128 bins
     (void)midbit4; (void)mb_shift; (void)mb_mul;
-    const uint32_t pk_mask4 = p.hist_entries * 4u - 1u;           // mode 5: byte offset of the word
-    const uint32_t pk_shift = 31u - __clz(p.hist_entries * 4u) - 4u;  // (c4 >> pk_shift) & 16 = 16 * upper-half bit
-    (void)pk_mask4; (void)pk_shift;
     using T = typename OutT<OUT>::type;
     T *out = reinterpret_cast<T *>(p.out);
     constexpr uint32_t FULL = 0xffffffffu;
@@ -723,7 +722,10 @@ seq_kernel(const SeqParams p) {
                                 idx4[j] = s4 - hi * mb_mul;
                             } else if constexpr (HIST_MODE == 5) {
                                 const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
-                                idx4[j] = p.canonical ? min(f4, r4) : f4;   // unpacked below
+                                const uint32_t c = min(f4, r4) >> 2;
+                                const uint32_t w = c >> 5;
+                                const uint32_t below = s_bitmap[w] & ((1u << (c & 31u)) - 1u);
+                                idx4[j] = (uint32_t)s_prefix[w] + (uint32_t)__popc(below);   // rank; word/half split below
                             } else if constexpr (HIST_MODE == 7) {
                                 const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
                                 const uint32_t c = min(f4, r4) >> 2;                 // canonical code (a, R)
@@ -747,10 +749,9 @@ seq_kernel(const SeqParams p) {
                             const bool all16 = __all_sync(FULL, vw == 0xFFFFu);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                const uint32_t c4 = idx4[j];
+                                const uint32_t rk = idx4[j];
                                 const uint32_t one = all16 ? 1u : ((vw >> (15 - j)) & 1u);
-                                atomicAdd(reinterpret_cast<uint32_t *>(hbytes + (c4 & pk_mask4)),
-                                          one << ((c4 >> pk_shift) & 16u));
+                                atomicAdd(hist + (rk >> 1), one << ((rk & 1u) << 4));
                             }
                             continue;
                         }

@@ -23,7 +23,7 @@ def comp(k):
 
 def check(k, bases, offsets, mins=True, norm_mode=NORM_CLI, dtype=np.float32, what="", **opts):
     oc = comp(k)
-    for key, dflt in (("force_path", 0), ("short_variant", 0), ("packed16", 0), ("even_rank", 1), ("dense_odd", 1)):
+    for key, dflt in (("force_path", 0), ("short_variant", 0), ("packed16", 1), ("even_rank", 1), ("dense_odd", 1)):
         oc.set_option(key, opts.get(key, dflt))
     n = len(offsets) - 1
     totals = np.zeros(n, dtype=np.uint64)
@@ -31,7 +31,7 @@ def check(k, bases, offsets, mins=True, norm_mode=NORM_CLI, dtype=np.float32, wh
     want, wtot = O.vectorise_batch(bases, offsets, k, mins, norm_mode)
     assert np.array_equal(totals, wtot), f"{what}: totals differ"
     assert_rows_equal(got, want, dtype, what)
-    for key, dflt in (("force_path", 0), ("short_variant", 0), ("packed16", 0), ("even_rank", 1), ("dense_odd", 1)):
+    for key, dflt in (("force_path", 0), ("short_variant", 0), ("packed16", 1), ("even_rank", 1), ("dense_odd", 1)):
         oc.set_option(key, dflt)
     return got
 
@@ -168,6 +168,8 @@ def test_alternative_histogram_modes_agree():
     rng = np.random.default_rng(66)
     lengths = np.r_[rng.integers(0, 6000, size=60), [40000, 90000]]
     bases, offsets = random_batch(rng, lengths, noise=0.002, n_runs=0.3)
+    check(8, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, packed16=0, what="k8 mode 7")
+    check(8, bases, offsets, norm_mode=NORM_CLI, dtype=np.float64, packed16=0, what="k8 mode 7 f64")
     check(8, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, even_rank=0, what="k8 mode 2")
     check(8, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, even_rank=0, what="k8 mode 2 f32")
     check(7, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, dense_odd=0, what="k7 mode 1")
