@@ -177,7 +177,8 @@ int launch_short(ktb_oligo *h, const ShortParams &p, const ShortCfg &c, cudaStre
 
 template <int OUT>
 int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st) {
-    const size_t smem = (hist_mode == 7 || hist_mode == 5) ? ((((size_t)p.hist_entries + 3) & ~(size_t)3) * 4 + (size_t)p.even_words * 6 + 16)
+    const size_t smem = (hist_mode == 5) ? ((((size_t)p.hist_entries + 3) & ~(size_t)3) * 4 + (size_t)p.even_words * 5 + 16)
+                        : (hist_mode == 7) ? ((((size_t)p.hist_entries + 3) & ~(size_t)3) * 4 + (size_t)p.even_words * 6 + 16)
                                          : (size_t)p.hist_entries * 4;
     void (*kern)(const SeqParams) = nullptr;
     const bool nrm = p.norm_mode != NORM_COUNTS;
@@ -205,9 +206,9 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     // per CTA (less barrier / priming overhead, occupancy is not the limit); long contigs and the big
     // histograms want 8 warps.
     const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
-    const int auto_threads = ((mean_len <= 16384 && smem <= 16 * 1024) ? 128 : 256);
+    const int auto_threads = ((mean_len <= 16384 && (smem <= 16 * 1024 || hist_mode == 5)) ? 128 : 256);
     int threads = h->seq_threads > 0 ? h->seq_threads : auto_threads;
-    if (hist_mode == 5 && threads > 512) threads = 512;
+    if (hist_mode == 5 && threads > 256) threads = 256;
     if (hist_mode != 2 && hist_mode != 5 && hist_mode != 7 && threads > KTB_SEQ_MAXTHREADS) threads = KTB_SEQ_MAXTHREADS;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;

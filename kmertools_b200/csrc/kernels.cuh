@@ -580,8 +580,8 @@ __device__ __forceinline__ void seq_write_row(uint32_t *hist, typename OutT<OUT>
 // KT: compile-time k (0 = use p.k); the specialised instances fold the window-mask loop and every
 // shift amount into immediates.
 template <int OUT, int HIST_MODE, bool NORM, int KT = 0>
-__global__ void __launch_bounds__((HIST_MODE == 2 || HIST_MODE == 7) ? 1024 : ((HIST_MODE == 5) ? 512 : KTB_SEQ_MAXTHREADS),
-                                  (HIST_MODE == 2 || HIST_MODE == 7) ? 1 : (HIST_MODE == 5) ? 2 : ((HIST_MODE == 4) ? KTB_SEQ_MINBLOCKS4 : KTB_SEQ_MINBLOCKS))
+__global__ void __launch_bounds__((HIST_MODE == 2 || HIST_MODE == 7) ? 1024 : ((HIST_MODE == 5) ? 256 : KTB_SEQ_MAXTHREADS),
+                                  (HIST_MODE == 2 || HIST_MODE == 7) ? 1 : (HIST_MODE == 5) ? 3 : ((HIST_MODE == 4) ? KTB_SEQ_MINBLOCKS4 : KTB_SEQ_MINBLOCKS))
 seq_kernel(const SeqParams p) {
     extern __shared__ __align__(16) uint32_t hist[];
     __shared__ unsigned long long s_group;
@@ -603,7 +603,11 @@ seq_kernel(const SeqParams p) {
     if constexpr (HIST_MODE == 7 || HIST_MODE == 5) {
         for (uint32_t i = tid; i < p.even_words; i += blockDim.x) s_bitmap[i] = __ldg(p.even_tab + i);
         const uint16_t *gp = reinterpret_cast<const uint16_t *>(p.even_tab + p.even_words);
-        for (uint32_t i = tid; i < p.even_words; i += blockDim.x) s_prefix[i] = gp[i];
+        if constexpr (HIST_MODE == 5) {   // every second prefix only: 2 KB less, which lets a third CTA fit on the SM
+            for (uint32_t i = tid; i < p.even_words / 2; i += blockDim.x) s_prefix[i] = gp[2 * i];
+        } else {
+            for (uint32_t i = tid; i < p.even_words; i += blockDim.x) s_prefix[i] = gp[i];
+        }
     }
     (void)s_bitmap; (void)s_prefix;
     if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
@@ -724,8 +728,11 @@ seq_kernel(const SeqParams p) {
                                 const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
                                 const uint32_t c = min(f4, r4) >> 2;
                                 const uint32_t w = c >> 5;
-                                const uint32_t below = s_bitmap[w] & ((1u << (c & 31u)) - 1u);
-                                idx4[j] = (uint32_t)s_prefix[w] + (uint32_t)__popc(below);   // rank; word/half split below
+                                const uint2 bw = reinterpret_cast<const uint2 *>(s_bitmap)[w >> 1];   // words w&~1, w|1
+                                const bool odd = (w & 1u) != 0u;
+                                const uint32_t below = (odd ? bw.y : bw.x) & ((1u << (c & 31u)) - 1u);
+                                idx4[j] = (uint32_t)s_prefix[w >> 1] + (uint32_t)__popc(below) +
+                                          (odd ? (uint32_t)__popc(bw.x) : 0u);   // rank; word/half split below
                             } else if constexpr (HIST_MODE == 7) {
                                 const uint32_t r4 = (uint32_t)(R64 >> (2 * (16 + j - (int)k))) & kmask4;
                                 const uint32_t c = min(f4, r4) >> 2;                 // canonical code (a, R)
