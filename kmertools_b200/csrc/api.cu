@@ -745,13 +745,14 @@ int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offs
         CU(cudaStreamSynchronize(s.stream));
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1])); h->stats.h2d_ms += ms;
-        CU(cudaEventElapsedTime(&ms, s.ev[1], s.ev[2])); h->stats.kernel_ms += ms;
+        CU(cudaEventElapsedTime(&ms, s.ev[4], s.ev[2])); h->stats.kernel_ms += ms;
         CU(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3])); h->stats.d2h_ms += ms;
         has[b] = false;
         return KTB_OK;
     };
 
     int b = 0;
+    cudaEvent_t prev_kernels_done = nullptr;
     const uint64_t launches_before = 0;
     (void)launches_before;
     uint64_t total_launches = 0;
@@ -783,6 +784,10 @@ int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offs
             CU(cudaGetLastError());
             total_launches++;
         }
+        // The work counters, reject lists and scratch rows live in the handle, not in the chunk set: the
+        // kernels of consecutive chunks must not overlap (copies still do).  Chain them with an event.
+        if (prev_kernels_done) CU(cudaStreamWaitEvent(s.stream, prev_kernels_done, 0));
+        CU(cudaEventRecord(s.ev[4], s.stream));
         const ktb_stats keep = h->stats;
         if (int rc = dispatch_device(h, (const uint8_t *)s.bases.p, (const uint64_t *)s.offsets.p, cn, nb,
                                      canonical, norm_mode, out_dtype, s.out.p,
@@ -790,6 +795,7 @@ int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offs
             return rc;
         total_launches += h->stats.launches - keep.launches;
         CU(cudaEventRecord(s.ev[2], s.stream));
+        prev_kernels_done = s.ev[2];
         CU(cudaMemcpyAsync((uint8_t *)out + i0 * row_bytes, s.out.p, cn * row_bytes, cudaMemcpyDeviceToHost,
                            s.stream));
         if (totals) CU(cudaMemcpyAsync(totals + i0, s.totals.p, cn * 8, cudaMemcpyDeviceToHost, s.stream));

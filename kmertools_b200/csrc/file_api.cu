@@ -74,9 +74,13 @@ struct Set {
     Pinned h_bases, h_offsets, h_out;
     Dev d_bases, d_offsets, d_counts, d_totals, d_text;
     cudaStream_t stream = nullptr;
+    cudaEvent_t kernels_done = nullptr;
     uint64_t n = 0, nbases = 0, out_bytes = 0;
     bool pending = false;
-    ~Set() { if (stream) cudaStreamDestroy(stream); }
+    ~Set() {
+        if (kernels_done) cudaEventDestroy(kernels_done);
+        if (stream) cudaStreamDestroy(stream);
+    }
 };
 
 // u32 counts -> "c0<d>c1<d>...\n" (format!("{}", f64) prints integral values without ".0", oligo.rs:138)
@@ -261,8 +265,11 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
 
     Set sets[2];
     for (auto &s : sets)
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess)
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.kernels_done, cudaEventDisableTiming) != cudaSuccess)
             return ktb_internal_fail(KTB_ERR_CUDA, "cudaStreamCreate failed");
+    cudaEvent_t prev_kernels_done = nullptr;   // the handle's work counters / scratch are shared: kernels of
+                                               // consecutive batches are chained, copies still overlap
     std::vector<char> text;
     uint64_t launches = 0;
 
@@ -330,6 +337,7 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
         cudaMemcpyAsync(s.d_offsets.p, s.h_offsets.p, (n + 1) * 8, cudaMemcpyHostToDevice, s.stream);
         const uint64_t l0 = ktb_internal_launches(h);
         (void)l0;
+        if (prev_kernels_done) cudaStreamWaitEvent(s.stream, prev_kernels_done, 0);
         const bool f64rows = cgr && norm;   // CGR prints the f64 quotient itself ("{}")
         if (int rc = ktb_internal_dispatch(h, (const uint8_t *)s.d_bases.p, (const uint64_t *)s.d_offsets.p, n, used,
                                            cgr ? 1 : o->canonical, f64rows ? KTB_NORM_CLI : KTB_NORM_COUNTS,
@@ -346,10 +354,13 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
                 (const uint32_t *)s.d_counts.p, (const uint64_t *)s.d_totals.p, (uint8_t *)s.d_text.p, n, (uint32_t)dim,
                 o->delim, KTB_NORM_CLI, o->canonical);
             ++launches;
+            cudaEventRecord(s.kernels_done, s.stream);
             cudaMemcpyAsync(s.h_out.p, s.d_text.p, s.out_bytes, cudaMemcpyDeviceToHost, s.stream);
         } else {
+            cudaEventRecord(s.kernels_done, s.stream);
             cudaMemcpyAsync(s.h_out.p, s.d_counts.p, s.out_bytes, cudaMemcpyDeviceToHost, s.stream);
         }
+        prev_kernels_done = s.kernels_done;
         if (cudaGetLastError() != cudaSuccess) return ktb_internal_fail(KTB_ERR_CUDA, "enqueue failed");
         s.pending = true;
         ++b;

@@ -219,6 +219,21 @@ def test_chunked_host_pipeline_matches():
         oc.set_option("chunk_bytes", 512 << 20)
 
 
+def test_chunked_pipeline_with_rejected_groups():
+    """Many small chunks whose kernels could overlap on different streams: the short-read kernel's reject list
+    and the work counters are shared by the handle, so consecutive chunks must be chained."""
+    rng = np.random.default_rng(13)
+    lengths = np.where(rng.random(40000) < 0.1, rng.integers(300, 3000, size=40000), 150)
+    bases, offsets = random_batch(rng, lengths, noise=0.001)
+    oc = comp(5)
+    oc.set_option("chunk_bytes", 1 << 19)  # 256 rows per chunk -> ~160 chunks
+    try:
+        for _ in range(3):
+            check(5, bases, offsets, dtype=np.float32, what="chunked mixed")
+    finally:
+        oc.set_option("chunk_bytes", 512 << 20)
+
+
 def test_survey_hashes_via_gpu(golden):
     """sha256 of the CLI text for k=3..7 x {canonical,raw} x {norm,counts}."""
     from tests.test_oracle import SURVEY_KATS
