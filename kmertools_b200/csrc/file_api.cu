@@ -336,7 +336,6 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
         cudaMemcpyAsync(s.d_bases.p, s.h_bases.p, used, cudaMemcpyHostToDevice, s.stream);
         cudaMemcpyAsync(s.d_offsets.p, s.h_offsets.p, (n + 1) * 8, cudaMemcpyHostToDevice, s.stream);
         const uint64_t l0 = ktb_internal_launches(h);
-        (void)l0;
         if (prev_kernels_done) cudaStreamWaitEvent(s.stream, prev_kernels_done, 0);
         const bool f64rows = cgr && norm;   // CGR prints the f64 quotient itself ("{}")
         if (int rc = ktb_internal_dispatch(h, (const uint8_t *)s.d_bases.p, (const uint64_t *)s.d_offsets.p, n, used,
@@ -344,7 +343,7 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
                                            f64rows ? KTB_OUT_F64 : KTB_OUT_U32, s.d_counts.p,
                                            (uint64_t *)s.d_totals.p, s.stream))
             return rc;
-        launches += ktb_internal_launches(h);
+        launches += ktb_internal_launches(h) - l0;
         if (gpu_text) {
             const uint64_t nel = n * dim;
             uint64_t grid = (nel + 255) / 256;
