@@ -273,6 +273,8 @@ def main():
     ap.add_argument("--dense-odd", type=int, default=None)
     ap.add_argument("--even-rank", type=int, default=None)
     ap.add_argument("--global-steps-per-warp", type=int, default=None)
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="any ktb_oligo_set_option key (repeatable)")
     args = ap.parse_args()
     spec = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -313,6 +315,9 @@ def main():
         oc.set_option("dense_odd", args.dense_odd)
     if args.global_wave_mb is not None:
         oc.set_option("global_wave_bytes", args.global_wave_mb << 20)
+    for kv in args.opt:
+        key, _, val = kv.partition("=")
+        oc.set_option(key, int(val))
     bases, offsets = make_workload(spec, args.scale, dev)
     n = offsets.numel() - 1
     total_bases = int(offsets[-1])

@@ -100,6 +100,8 @@ struct ktb_oligo {
     uint32_t *d_mb_perm = nullptr;
     uint32_t *d_even_tab = nullptr;        // even k: bitmap words + u16 prefixes for the in-kernel rank (mode 7)
     uint32_t even_words = 0;
+    uint32_t *d_wave_tab = nullptr;        // canonical-code bitmap + u32 pair prefixes for wave_kernel<2>
+    uint32_t wave_tab_words = 0;
     uint64_t mb_entries = 0;               // histogram words mode 4 needs (dense index + skew)
     uint32_t *d_short_tab_canon = nullptr; // [4^k] (k <= 5): (word byte offset << 22) | 8*(bin&3)
     uint32_t *d_short_tab_raw = nullptr;
@@ -120,6 +122,9 @@ struct ktb_oligo {
     int even_rank = 1;    // use seq_kernel mode 7 where it applies
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
     int global_steps_per_warp = 1;
+    int wave_persistent = 1;                 // global-atomic path as one cooperative launch (u32 / f32 output)
+    int64_t wave_budget_bytes = 96ll << 20;  // three waves of the cooperative kernel (zeroed / counted / normalised)
+    int wave_smem_rank = 1;                  // rank from shared-memory tables when they fit (k <= 10)
     int64_t global_wave_bytes = 64ll << 20;  // rows zeroed + counted together in the global-atomic path (fits L2)
     ktb_stats stats{};
 };
@@ -338,6 +343,31 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
             h->stats.launches++;
         }
         if (int rc = finalize(counts, 0, n)) return rc;
+    } else if (h->wave_persistent && OUT != OUT_F64 && n > 0) {
+        // One persistent cooperative launch: the wave loop (zero next rows / count / normalise previous rows)
+        // runs on the device with a grid barrier per wave instead of three launches per wave.
+        WaveParams wp{};
+        wp.bases = d_bases; wp.offsets = d_offsets; wp.n = n; wp.total_bases = total_bases;
+        wp.rows = (uint32_t *)d_out; wp.totals = tot;
+        wp.rank_full = canonical ? h->d_rank_full : nullptr;
+        wp.dim = dim; wp.k = (uint32_t)h->k; wp.norm_mode = norm_mode; wp.canonical = canonical;
+        wp.out_f32 = (OUT == OUT_F32) ? 1 : 0;
+        // three waves are live in L2 at once (being zeroed, counted, normalised)
+        wp.wave_rows = std::max<uint64_t>(1, std::min<uint64_t>(256, (uint64_t)h->wave_budget_bytes / 3 / row_bytes));
+        const int rank_mode = !canonical ? 0 : (h->d_wave_tab && h->wave_smem_rank) ? 2 : 1;
+        wp.rank_tab = h->d_wave_tab; wp.tab_words = h->wave_tab_words;
+        const void *kern = rank_mode == 0 ? (const void *)wave_kernel<0>
+                         : rank_mode == 1 ? (const void *)wave_kernel<1> : (const void *)wave_kernel<2>;
+        const int threads = 1024;
+        const size_t smem = rank_mode == 2 ? ((size_t)h->wave_tab_words * 6 + 16) : 0;
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+        if (per_sm < 1) return fail(KTB_ERR_CUDA, "wave_kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+        const unsigned grid = (unsigned)h->sm_count;   // one CTA per SM: the RED rate of an SM does not grow with occupancy
+        void *args[] = {&wp};
+        CU(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, st));
+        h->stats.launches++;
     } else {
         // Waves of rows that fit L2 together: zero the wave's rows, let every CTA of the GPU work on that
         // wave (sequences are split into tiles), normalise it, move on.  The REDs then hit rows that are
@@ -573,6 +603,27 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
             CUB(cudaMemcpy(h->d_mb_perm, mbp.data(), mbp.size() * 4, cudaMemcpyHostToDevice));
         }
     }
+    {   // wave_kernel<2>: rank(c) = prefix[w / 2] + popc(bits below c) for canonical c, tables in shared memory
+        const uint64_t words = h->ncodes / 32;
+        const uint64_t bytes = words * 4 + (words / 2) * 4;
+        if (h->ncodes >= 64 && h->dim_canon * 4 > 64 * 1024 && bytes + 4096 <= h->smem_optin) {
+            std::vector<uint32_t> tab(words + words / 2, 0);
+            uint32_t running = 0;
+            for (uint64_t w = 0; w < words; ++w) {
+                if (!(w & 1)) tab[words + w / 2] = running;
+                uint32_t bits = 0;
+                for (uint32_t i = 0; i < 32; ++i) {
+                    const uint64_t x = 32 * w + i;
+                    if (x <= rev_comp(x, k)) bits |= 1u << i;
+                }
+                tab[w] = bits;
+                running += (uint32_t)__builtin_popcount(bits);
+            }
+            h->wave_tab_words = (uint32_t)words;
+            CUB(cudaMalloc(&h->d_wave_tab, tab.size() * 4));
+            CUB(cudaMemcpy(h->d_wave_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
     if (h->ncodes <= (uint64_t)ktb::SHORT_MAX_CODES) {
         std::vector<uint32_t> tc(h->ncodes), tr(h->ncodes);
         for (uint64_t x = 0; x < h->ncodes; ++x) {
@@ -627,6 +678,7 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     if (h->d_mb_of_rank) cudaFree(h->d_mb_of_rank);
     if (h->d_mb_perm) cudaFree(h->d_mb_perm);
     if (h->d_even_tab) cudaFree(h->d_even_tab);
+    if (h->d_wave_tab) cudaFree(h->d_wave_tab);
     if (h->d_short_tab_canon) cudaFree(h->d_short_tab_canon);
     if (h->d_short_tab_raw) cudaFree(h->d_short_tab_raw);
     if (h->d_counters) cudaFree(h->d_counters);
@@ -685,6 +737,13 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->dense_odd = (int)value;
     } else if (!strcmp(key, "global_steps_per_warp")) {
         h->global_steps_per_warp = (int)value;
+    } else if (!strcmp(key, "wave_persistent")) {
+        h->wave_persistent = value != 0;
+    } else if (!strcmp(key, "wave_smem_rank")) {
+        h->wave_smem_rank = value != 0;
+    } else if (!strcmp(key, "wave_budget_bytes")) {
+        if (value < 1) return fail(KTB_ERR_ARG, "wave_budget_bytes must be positive");
+        h->wave_budget_bytes = value;
     } else if (!strcmp(key, "global_wave_bytes")) {
         if (value < 1) return fail(KTB_ERR_ARG, "global_wave_bytes must be positive");
         h->global_wave_bytes = value;

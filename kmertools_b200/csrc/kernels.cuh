@@ -23,6 +23,7 @@
 //   finalize_kernel: u32 counts -> f32 / f64 rows for mode 3.
 //   flat_kernel   : flat decomposition of the base stream + global atomics; cross-check only (force_path=1).
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -801,6 +802,234 @@ seq_kernel(const SeqParams p) {
             __syncthreads();
         }
     }
+}
+
+// ================================================================================================
+// wave_kernel — histograms larger than shared memory, ONE persistent cooperative launch
+// ================================================================================================
+// Same arithmetic as seq_kernel mode 3 (RED atomics straight into zeroed u32 rows), but the wave loop lives on
+// the device.  A wave is a run of rows small enough that the wave being counted, the next one (zeroed at the
+// end of the iteration) and the previous one (normalised, f32 only) stay in L2 together, so a row reaches HBM
+// once (ncu: DRAM writes = 1.1 x the output, reads = the bases).  Iteration w of every CTA:
+//     step table of wave w  ->  RED the items of wave w  ->  zero wave w+1, normalise wave w-1  ->  grid barrier
+// Work item = one 32-chunk step (512 bases) of one sequence, taken by a WARP; items are dealt round-robin over
+// the CTAs so that every SM issues REDs: scattered REDs leave an SM at ~0.66 lanes/clock whatever the occupancy
+// (tools/microbench_red.cu: 190 G/s chip-wide), which is the bound of the counting phase.
+// Replaces ~3 launches per wave (row memset, counter memset, kernel) whose latency dominated the k = 10 path.
+// Measured and NOT faster (profiles/r1k_wave_kernel_experiments.txt): flag-based split-phase barriers, warp-
+// specialised zeroing with several waves in flight, prefetching the first item across the barrier, one zero
+// store behind every RED.  A poll or dependent load queues behind the SM's own RED backlog, so every cross-SM
+// hand-off costs microseconds, and zeroing ahead of the counting doubles the L2 footprint (about 64 MB is usable
+// for this pattern), which halves the wave and doubles the number of barriers.
+// Output u32 or f32 in place; f64 keeps the multi-launch path.
+struct WaveParams {
+    const uint8_t *bases;
+    const uint64_t *offsets;
+    uint64_t n;
+    uint64_t total_bases;
+    uint32_t *rows;               // n x dim u32 (u32 / f32 output written in place)
+    unsigned long long *totals;   // n, zeroed before the launch
+    const uint32_t *rank_full;    // RANK 1: [4^k]
+    const uint32_t *rank_tab;     // RANK 2: canonical-code bitmap (tab_words) + u32 prefix per PAIR of words
+    uint32_t tab_words;
+    uint64_t dim;
+    uint64_t wave_rows;           // sequences per wave (<= 256)
+    uint32_t k;
+    int norm_mode;
+    int canonical;
+    int out_f32;                  // 0: leave u32 counts, 1: convert rows to f32 (normalised or not) in place
+};
+
+// zero rows [s0, s1): thread `t` of `nt`
+__device__ __forceinline__ void wave_zero_rows(const WaveParams &p, uint64_t s0, uint64_t s1, uint64_t t, uint64_t nt) {
+    if (s0 >= s1) return;
+    uint4 *dst = reinterpret_cast<uint4 *>(p.rows + s0 * p.dim);
+    const uint64_t nvec = (s1 - s0) * p.dim / 4;   // dim % 4 == 0 on this path
+    for (uint64_t i = t; i < nvec; i += nt) dst[i] = make_uint4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ float4 wave_cvt4(const WaveParams &p, uint4 c, unsigned long long total) {
+    const bool norm = p.norm_mode != NORM_COUNTS;
+    const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
+    const float dF = (float)dv, rinv = __frcp_rn(dF);
+    const double dD = (double)dv;
+    float4 o;
+    if (!norm) {
+        o.x = cvt_count<OUT_F32, false, true>(c.x, dF, rinv, dD);
+        o.y = cvt_count<OUT_F32, false, true>(c.y, dF, rinv, dD);
+        o.z = cvt_count<OUT_F32, false, true>(c.z, dF, rinv, dD);
+        o.w = cvt_count<OUT_F32, false, true>(c.w, dF, rinv, dD);
+    } else if (dv < (1ULL << 23)) {
+        o.x = cvt_count<OUT_F32, true, true>(c.x, dF, rinv, dD);
+        o.y = cvt_count<OUT_F32, true, true>(c.y, dF, rinv, dD);
+        o.z = cvt_count<OUT_F32, true, true>(c.z, dF, rinv, dD);
+        o.w = cvt_count<OUT_F32, true, true>(c.w, dF, rinv, dD);
+    } else {
+        o.x = cvt_count<OUT_F32, true, false>(c.x, dF, rinv, dD);
+        o.y = cvt_count<OUT_F32, true, false>(c.y, dF, rinv, dD);
+        o.z = cvt_count<OUT_F32, true, false>(c.z, dF, rinv, dD);
+        o.w = cvt_count<OUT_F32, true, false>(c.w, dF, rinv, dD);
+    }
+    return o;
+}
+
+// counts -> f32 in place for rows [s0, s1): thread `t` of `nt`, 2 independent 16-byte loads in flight per thread
+__device__ __forceinline__ void wave_finalize_rows(const WaveParams &p, uint64_t s0, uint64_t s1, uint64_t t, uint64_t nt) {
+    if (s0 >= s1 || !p.out_f32) return;
+    constexpr int U = 2;
+    const uint64_t nvec = (s1 - s0) * p.dim / 4;
+    uint4 *buf = reinterpret_cast<uint4 *>(p.rows + s0 * p.dim);
+    for (uint64_t i0 = t; i0 < nvec; i0 += U * nt) {
+        uint4 c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * nt;
+            if (i < nvec) c[u] = __ldcg(buf + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * nt;
+            if (i < nvec)
+                reinterpret_cast<float4 *>(buf)[i] = wave_cvt4(p, c[u], __ldcg(p.totals + s0 + (i * 4) / p.dim));
+        }
+    }
+}
+
+// RANK: 0 raw codes, 1 rank through the L2-resident table, 2 rank computed from shared-memory tables (one
+// look-up + RED per k-mer through L2 halves to the RED alone; the tables fit up to k = 10).
+template <int RANK>
+__global__ void __launch_bounds__(1024) wave_kernel(const WaveParams p) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) uint32_t s_tab[];   // RANK 2: bitmap words, then pair prefixes
+    __shared__ uint32_t s_steps[256 + 1];   // exclusive prefix of 32-chunk steps per sequence of the wave (<= 256 rows)
+    __shared__ uint32_t s_wsum[8];
+    if constexpr (RANK == 2) {
+        const uint32_t nw = p.tab_words + p.tab_words / 2;
+        for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) s_tab[i] = __ldg(p.rank_tab + i);
+    }
+    const uint32_t *s_prefix = s_tab + p.tab_words;
+    (void)s_prefix;
+    __syncthreads();
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t k = p.k;
+    const uint32_t kmask = (1u << (2 * k)) - 1u;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t G = gridDim.x;
+    const uint64_t slot = (uint64_t)(tid >> 5) * G + blockIdx.x;   // consecutive items on different SMs
+    const uint64_t nslots = (uint64_t)G * (blockDim.x >> 5);
+    const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + tid, gnt = (uint64_t)G * blockDim.x;
+    const uint64_t nwaves = (p.n + p.wave_rows - 1) / p.wave_rows;
+    const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+    auto wave_lo = [&](uint64_t w) { return min(p.n, w * p.wave_rows); };
+
+    // step table of wave w into s_steps; returns the number of (sequence, step) items.  All threads call.
+    auto build_table = [&](uint64_t w) -> uint32_t {
+        const uint64_t s0 = wave_lo(w);
+        const uint32_t rows = (uint32_t)(wave_lo(w + 1) - s0);
+        uint32_t *tab = s_steps;
+        uint32_t mysteps = 0;
+        if ((uint32_t)tid < rows) {
+            const uint64_t a = p.offsets[s0 + tid], b = p.offsets[s0 + tid + 1];
+            const uint32_t nch = (b - a >= k) ? (uint32_t)(((b - 1) >> 4) - (a >> 4)) + 1u : 0u;
+            mysteps = (nch + 31) >> 5;
+        }
+        uint32_t incl = mysteps;   // inclusive scan over the first 256 threads
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31 && tid < 256) s_wsum[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t base = 0;
+            for (int ww = 0; ww < (tid >> 5); ++ww) base += s_wsum[ww];
+            tab[tid + 1] = base + incl;
+        }
+        if (tid == 0) tab[0] = 0;
+        __syncthreads();
+        return tab[rows];
+    };
+    // one item: find its (sequence, step) in the table, load 16 bases per lane, RED the windows that end in them
+    auto do_item = [&](uint64_t w, uint32_t item) {
+        const uint64_t s0 = wave_lo(w);
+        const uint32_t rows = (uint32_t)(wave_lo(w + 1) - s0);
+        uint32_t lo = 0, hi = rows;   // largest r with s_steps[r] <= item
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_steps[mid] <= item) lo = mid; else hi = mid;
+        }
+        const uint64_t seq = s0 + lo;
+        const uint32_t step = item - s_steps[lo];
+        const uint64_t q0 = p.offsets[seq], q1 = p.offsets[seq + 1];
+        const uint64_t cbase = q0 >> 4;
+        const uint32_t nch = (uint32_t)(((q1 - 1) >> 4) - cbase) + 1u;
+        const uint32_t c = step * 32u + lane;
+        const uint4 v = (c < nch) ? load16_guarded(p.bases, (cbase + c) << 4, p.total_bases) : filler;
+        // the chunk before this step belongs to another warp's item: re-read it for the windows that straddle
+        const uint4 vp = (lane == 0 && c > 0) ? load16_guarded(p.bases, (cbase + c - 1) << 4, p.total_bases) : filler;
+        uint32_t cf, vm;
+        decode16(v, cf, vm);
+        if (c >= nch) vm = 0;
+        if (c == 0) vm &= 0xFFFFu >> (uint32_t)(q0 & 15);
+        if (c == nch - 1) vm &= ~(0xFFFFu >> ((uint32_t)((q1 - 1) & 15) + 1u)) & 0xFFFFu;
+        uint32_t cf_prev = __shfl_up_sync(FULL, cf, 1);
+        uint32_t vm_prev = __shfl_up_sync(FULL, vm, 1);
+        if (lane == 0) {
+            cf_prev = 0; vm_prev = 0;
+            if (c > 0) {
+                decode16(vp, cf_prev, vm_prev);
+                if (c - 1 == 0) vm_prev &= 0xFFFFu >> (uint32_t)(q0 & 15);
+            }
+        }
+        const uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
+        uint32_t cnt = __popc(vw);
+        const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
+        uint32_t *row = p.rows + seq * p.dim;
+        uint32_t idx[16];   // all 16 ranks before the first RED (f is always a valid code, also for invalid windows)
+        uint64_t R64 = 0;
+        if constexpr (RANK == 2) R64 = ((uint64_t)revcomp_pack(cf) << 32) | revcomp_pack(cf_prev);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t f = (uint32_t)(F64 >> (2 * (15 - j))) & kmask;
+            if constexpr (RANK == 0) {
+                idx[j] = f;
+            } else if constexpr (RANK == 1) {
+                idx[j] = __ldg(p.rank_full + f);
+            } else {
+                const uint32_t r = (uint32_t)(R64 >> (2 * (17 + j - (int)k))) & kmask;
+                const uint32_t cc = min(f, r);
+                const uint32_t wd = cc >> 5;
+                const uint2 bw = reinterpret_cast<const uint2 *>(s_tab)[wd >> 1];
+                const bool odd = (wd & 1u) != 0u;
+                const uint32_t below = (odd ? bw.y : bw.x) & ((1u << (cc & 31u)) - 1u);
+                idx[j] = s_prefix[wd >> 1] + (uint32_t)__popc(below) + (odd ? (uint32_t)__popc(bw.x) : 0u);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (vw & (1u << (15 - j))) atomicAdd(row + idx[j], 1u);
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) cnt += __shfl_xor_sync(FULL, cnt, sft);
+        if (lane == 0 && cnt) atomicAdd(p.totals + seq, (unsigned long long)cnt);
+    };
+
+    wave_zero_rows(p, 0, wave_lo(1), gt, gnt);
+    grid.sync();
+    for (uint64_t w = 0; w < nwaves; ++w) {
+        const uint32_t nitems = build_table(w);
+        for (uint64_t item = slot; item < nitems; item += nslots) {
+            do_item(w, (uint32_t)item);
+        }
+        // warps without an item start here at once, so the zeroing overlaps the REDs of the others; the zeroed
+        // wave only has to stay in L2 from now on, which is why a wave can be as large as a third of L2
+        wave_zero_rows(p, wave_lo(w + 1), wave_lo(w + 2), gt, gnt);
+        if (w > 0) wave_finalize_rows(p, wave_lo(w - 1), wave_lo(w), gt, gnt);
+        grid.sync();
+    }
+    if (nwaves > 0) wave_finalize_rows(p, wave_lo(nwaves - 1), p.n, gt, gnt);
 }
 
 // ================================================================================================

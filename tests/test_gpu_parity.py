@@ -21,9 +21,14 @@ def comp(k):
     return _cache[k]
 
 
+OPTION_DEFAULTS = (("force_path", 0), ("short_variant", 0), ("packed16", 1), ("even_rank", 1), ("dense_odd", 1),
+                   ("wave_persistent", 1), ("wave_smem_rank", 1), ("wave_budget_bytes", 96 << 20),
+                   ("global_wave_bytes", 64 << 20))
+
+
 def check(k, bases, offsets, mins=True, norm_mode=NORM_CLI, dtype=np.float32, what="", **opts):
     oc = comp(k)
-    for key, dflt in (("force_path", 0), ("short_variant", 0), ("packed16", 1), ("even_rank", 1), ("dense_odd", 1)):
+    for key, dflt in OPTION_DEFAULTS:
         oc.set_option(key, opts.get(key, dflt))
     n = len(offsets) - 1
     totals = np.zeros(n, dtype=np.uint64)
@@ -31,7 +36,7 @@ def check(k, bases, offsets, mins=True, norm_mode=NORM_CLI, dtype=np.float32, wh
     want, wtot = O.vectorise_batch(bases, offsets, k, mins, norm_mode)
     assert np.array_equal(totals, wtot), f"{what}: totals differ"
     assert_rows_equal(got, want, dtype, what)
-    for key, dflt in (("force_path", 0), ("short_variant", 0), ("packed16", 1), ("even_rank", 1), ("dense_odd", 1)):
+    for key, dflt in OPTION_DEFAULTS:
         oc.set_option(key, dflt)
     return got
 
@@ -185,6 +190,27 @@ def test_large_k_global_path(k):
     check(k, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, what=f"k{k} f32")
     if k == 9:
         check(k, bases, offsets, norm_mode=NORM_CLI, dtype=np.float64, what=f"k{k} f64")
+
+
+@pytest.mark.parametrize("persistent", [1, 2, 0])
+@pytest.mark.parametrize("k,mins", [(9, True), (10, True), (11, True), (8, False)])
+def test_global_path_many_waves(k, mins, persistent):
+    """Histograms larger than shared memory with a wave budget of a few rows: many waves, ragged last wave,
+    empty / shorter-than-k sequences inside a wave, as one cooperative launch and as the multi-launch variant."""
+    rng = np.random.default_rng(700 + k)
+    lengths = np.r_[rng.integers(0, 4000, size=20), [0, k - 1, k, 30000], rng.integers(500, 9000, size=9)]
+    bases, offsets = random_batch(rng, lengths, noise=0.003, n_runs=0.2)
+    dim = (4 ** k if not mins else (4 ** k + (4 ** (k // 2) if k % 2 == 0 else 0)) // 2)
+    for rows_per_wave in (1, 3, 8):
+        budget = 3 * rows_per_wave * dim * 4 + 64
+        # 1: cooperative launch, rank from shared-memory tables (k <= 10); 2: rank through the L2 table; 0: multi-launch
+        opts = dict(wave_persistent=min(persistent, 1), wave_smem_rank=int(persistent == 1), global_wave_bytes=budget,
+                    wave_budget_bytes=budget)
+        check(k, bases, offsets, mins=mins, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"k{k} waves u32", **opts)
+        check(k, bases, offsets, mins=mins, norm_mode=NORM_CLI, dtype=np.float32, what=f"k{k} waves f32", **opts)
+    check(k, bases, offsets, mins=mins, norm_mode=NORM_PY, dtype=np.float32, what=f"k{k} py f32", **opts)
+    if k == 9:
+        check(k, bases, offsets, mins=mins, norm_mode=NORM_CLI, dtype=np.float64, what=f"k{k} f64", **opts)
 
 
 @pytest.mark.parametrize("k", [3, 5, 7])
