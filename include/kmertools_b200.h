@@ -90,6 +90,19 @@ int ktb_oligo_header(const ktb_oligo *h, int canonical, char *buf, size_t cap);
  * (canonical code -> rank, 0 elsewhere), pos_to_kmer has dim(canonical) entries.  Either may be NULL. */
 int ktb_oligo_pos_maps(const ktb_oligo *h, uint64_t *pos_map, uint64_t *pos_to_kmer, uint64_t *count);
 
+/* Replaces KmerGenerator::new + the whole iteration of KmerGenerator::next (kmer/src/kmer.rs:30-41,80-106;
+ * pybindings/src/kmer.rs:22-44): every window of `seq` whose k bases are unambiguous, in position order, as the
+ * forward code (first base most significant, A=0 C=1 G=2 T=3) and the code of its reverse complement.
+ * 1 <= k <= 31 as in the reference.  HOST buffers; `*count` receives the number of valid windows, the first
+ * min(*count, cap) pairs are written (cap = 0 with NULL arrays just counts; len - k + 1 always suffices). */
+int ktb_kmer_pairs(const uint8_t *seq, uint64_t len, int k, int device, uint64_t *out_f, uint64_t *out_r,
+                   uint64_t cap, uint64_t *count);
+
+/* Same on DEVICE buffers of the current device, enqueued on `stream` (a cudaStream_t; NULL = default stream);
+ * scratch comes from the stream-ordered allocator.  Returns after enqueueing. */
+int ktb_kmer_pairs_device(const uint8_t *d_seq, uint64_t len, int k, uint64_t *d_out_f, uint64_t *d_out_r,
+                          uint64_t cap, uint64_t *d_count, void *stream);
+
 /* Replaces OligoComputer::vectorise_one applied to a whole batch (pybindings vectorise_batch,
  * pybindings/src/oligo.rs:77-81; the rayon map in composition/src/oligo.rs:126-143).
  *

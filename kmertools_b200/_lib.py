@@ -51,6 +51,8 @@ SYMBOLS = {
     "ktb_oligo_dim": (_U64, [_VP, _I]),
     "ktb_oligo_header": (_I, [_VP, _I, C.c_char_p, _SZ]),
     "ktb_oligo_pos_maps": (_I, [_VP, _VP, _VP, C.POINTER(_U64)]),
+    "ktb_kmer_pairs": (_I, [_VP, _U64, _I, _I, _VP, _VP, _U64, C.POINTER(_U64)]),
+    "ktb_kmer_pairs_device": (_I, [_VP, _U64, _I, _VP, _VP, _U64, _VP, _VP]),
     "ktb_oligo_vectorise": (_I, [_VP, _VP, _VP, _U64, _I, _I, _I, _VP, _VP]),
     "ktb_oligo_vectorise_device": (_I, [_VP, _VP, _VP, _U64, _U64, _I, _I, _I, _VP, _VP, _VP]),
     "ktb_oligo_last_stats": (_I, [_VP, C.POINTER(Stats)]),

@@ -54,6 +54,25 @@ def test_argument_errors_without_gpu():
             OligoComputer(4)
 
 
+def test_kmer_pairs_argument_errors_without_gpu():
+    L = _lib.load()
+    n = C.c_uint64(7)
+    seq = (C.c_uint8 * 4)(*b"ACGT")
+    assert L.ktb_kmer_pairs(seq, 4, 0, 0, None, None, 0, C.byref(n)) == _lib.KTB_ERR_ARG
+    assert L.ktb_kmer_pairs(seq, 4, 32, 0, None, None, 0, C.byref(n)) == _lib.KTB_ERR_ARG
+    assert b"1..31" in L.ktb_last_error()
+    assert L.ktb_kmer_pairs(seq, 4, 2, 0, None, None, 0, None) == _lib.KTB_ERR_ARG
+    assert L.ktb_kmer_pairs(seq, 4, 2, 0, None, None, 3, C.byref(n)) == _lib.KTB_ERR_ARG
+    if L.ktb_device_count() == 0:
+        assert L.ktb_kmer_pairs(seq, 4, 2, 0, None, None, 0, C.byref(n)) == _lib.KTB_ERR_NODEVICE
+        from kmertools_b200 import KmerGenerator, KtbError
+        with pytest.raises(KtbError):
+            next(KmerGenerator("ACGT", 2))
+    with pytest.raises(ValueError):
+        from kmertools_b200 import KmerGenerator
+        KmerGenerator("ACGT", 0)
+
+
 def test_utils_mirror():  # tests/test_utils.py of the reference
     from pykmertools import utils
     assert utils.to_acgt(111, 5) == "ACGTT"
