@@ -435,6 +435,7 @@ def main():
 
     # ---- CPU baseline on rank 0 (bounded sample)
     cpu = None
+    parity = None
     if rank == 0 and not args.no_cpu:
         try:
             os.sched_setaffinity(0, range(os.cpu_count() or 1))   # the CPU arm uses every host core
@@ -448,6 +449,15 @@ def main():
         mean_len = max(1, total_bases // n)
         budget = max(64, int(cores * 0.01e9 * 3 / mean_len))   # same bounded sample as --impl reference (~3 s)
         gb, used, ns, dt = cpu_sample(spec, bh, oh, budget)
+        # the oracle as checker (SURVEY §8d "parity checks in every run"): the device-path rows of the first
+        # sequences of the workload against the CPU restatement, counts exact, f32 = (float)(f64 quotient)
+        from oracle import oracle as O
+        m = int(min(n, 10_000, max(1, 50_000_000 // mean_len), max(1, (1 << 28) // (dim * 8))))
+        po = np.ascontiguousarray(oh[: m + 1]).astype(np.uint64)
+        want, _ = O.vectorise_batch(bh[: int(po[-1])], po, k, True, spec["norm"])
+        got = out[:m].cpu().numpy().view(npdt)
+        parity = {"sequences": m, "exact": bool(np.array_equal(got, want.astype(npdt))),
+                  "rule": "u32 counts equal; f32 rows equal (float)(oracle f64 row), 0 ulp"}
         cpu = {"value": gb, "unit": "Gbases/s", "cores": used, "kind": "port",
                "sample": f"first {ns} sequences of the workload, {dt:.2f} s, C+OpenMP restatement of the reference "
                          f"(Rust reference not buildable in this image)"}
@@ -490,7 +500,7 @@ def main():
                        "l2": "inputs+outputs per step exceed L2 (126 MB)" if B > 4 * 126e6 else "small working set"},
             "sequences_per_s": world * n / (ms_per_step * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "cli": cli, "clocks": clocks,
-            "gpu_launches": int(launches_per_step * args.steps), "rows_sum_to_one": ok,
+            "gpu_launches": int(launches_per_step * args.steps), "rows_sum_to_one": ok, "parity": parity,
         }
         print(json.dumps(line))
     if world > 1:
