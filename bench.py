@@ -46,6 +46,11 @@ WORKLOADS = {
                         desc="100k x 10kbp, k=8 canonical u32 counts (BASELINE configs[4] i)"),
     "reads100k_k10": dict(n=2_000, length=100_000, k=10, dtype="u32", norm=0, seed=20250005,
                           desc="2k x 100kbp, k=10 canonical u32 counts, global-atomic path (configs[4] ii)"),
+    "reads100k_k10_f32": dict(n=2_000, length=100_000, k=10, dtype="f32", norm=1, seed=20250005,
+                              desc="2k x 100kbp, k=10 canonical f32 normalised (probe of the in-place normalisation, "
+                                   "not a BASELINE config)"),
+    "reads100k_k9": dict(n=8_000, length=100_000, k=9, dtype="u32", norm=0, seed=20250006,
+                         desc="8k x 100kbp, k=9 canonical u32 counts (probe, not a BASELINE config)"),
 }
 DT = {"u32": (0, np.uint32, 4), "f32": (1, np.float32, 4), "f64": (2, np.float64, 8)}
 

@@ -138,7 +138,7 @@ int ktb_oligo_last_stats(const ktb_oligo *h, ktb_stats *out);
  *   "wave_persistent"    1 (default): histograms larger than shared memory (k >= 9, raw k >= 8) are counted by one
  *                        cooperative launch for u32 / f32 output; 0: one memset + kernel (+ normalise) per wave
  *   "wave_smem_rank"     1 (default): that kernel computes canonical ranks from shared-memory tables (k <= 10)
- *   "wave_budget_bytes"  bytes of three waves of that kernel (being zeroed / counted / normalised; fits L2)
+ *   "wave_budget_bytes"  L2 budget of that kernel; a wave (rows zeroed, counted and normalised together) is a third of it
  *   "global_wave_bytes"  bytes of output rows zeroed + counted together by the multi-launch variant (fits L2)
  *   "short_warps", "short_variant"  accepted for compatibility with earlier revisions, no effect on results */
 int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value);

@@ -123,7 +123,7 @@ struct ktb_oligo {
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
     int global_steps_per_warp = 1;
     int wave_persistent = 1;                 // global-atomic path as one cooperative launch (u32 / f32 output)
-    int64_t wave_budget_bytes = 96ll << 20;  // three waves of the cooperative kernel (zeroed / counted / normalised)
+    int64_t wave_budget_bytes = 96ll << 20;  // L2 budget of the cooperative kernel, a wave is a third of it
     int wave_smem_rank = 1;                  // rank from shared-memory tables when they fit (k <= 10)
     int64_t global_wave_bytes = 64ll << 20;  // rows zeroed + counted together in the global-atomic path (fits L2)
     ktb_stats stats{};
@@ -351,13 +351,14 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         wp.rows = (uint32_t *)d_out; wp.totals = tot;
         wp.rank_full = canonical ? h->d_rank_full : nullptr;
         wp.dim = dim; wp.k = (uint32_t)h->k; wp.norm_mode = norm_mode; wp.canonical = canonical;
-        wp.out_f32 = (OUT == OUT_F32) ? 1 : 0;
-        // three waves are live in L2 at once (being zeroed, counted, normalised)
+        // a wave is a third of the budget: the wave being counted and the next one (zeroed at the end of the
+        // iteration) are live together, the rest is slack for lines on their way out (32 MB waves measured best)
         wp.wave_rows = std::max<uint64_t>(1, std::min<uint64_t>(256, (uint64_t)h->wave_budget_bytes / 3 / row_bytes));
         const int rank_mode = !canonical ? 0 : (h->d_wave_tab && h->wave_smem_rank) ? 2 : 1;
         wp.rank_tab = h->d_wave_tab; wp.tab_words = h->wave_tab_words;
-        const void *kern = rank_mode == 0 ? (const void *)wave_kernel<0>
-                         : rank_mode == 1 ? (const void *)wave_kernel<1> : (const void *)wave_kernel<2>;
+        constexpr bool F32 = (OUT == OUT_F32);
+        const void *kern = rank_mode == 0 ? (const void *)wave_kernel<0, F32>
+                         : rank_mode == 1 ? (const void *)wave_kernel<1, F32> : (const void *)wave_kernel<2, F32>;
         const int threads = 1024;
         const size_t smem = rank_mode == 2 ? ((size_t)h->wave_tab_words * 6 + 16) : 0;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

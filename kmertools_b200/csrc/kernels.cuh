@@ -808,10 +808,11 @@ seq_kernel(const SeqParams p) {
 // wave_kernel — histograms larger than shared memory, ONE persistent cooperative launch
 // ================================================================================================
 // Same arithmetic as seq_kernel mode 3 (RED atomics straight into zeroed u32 rows), but the wave loop lives on
-// the device.  A wave is a run of rows small enough that the wave being counted, the next one (zeroed at the
-// end of the iteration) and the previous one (normalised, f32 only) stay in L2 together, so a row reaches HBM
-// once (ncu: DRAM writes = 1.1 x the output, reads = the bases).  Iteration w of every CTA:
-//     step table of wave w  ->  RED the items of wave w  ->  zero wave w+1, normalise wave w-1  ->  grid barrier
+// the device.  A wave is a run of rows small enough that the wave being counted and the next one (zeroed at the
+// end of the iteration) stay in L2 together, so a row reaches HBM once (ncu: DRAM writes = 1.1 x the output,
+// reads = the bases).  Iteration w of every CTA:
+//     step table of wave w  ->  RED the items of wave w  ->  [f32: grid barrier, normalise wave w in place]
+//     ->  zero wave w+1  ->  grid barrier
 // Work item = one 32-chunk step (512 bases) of one sequence, taken by a WARP; items are dealt round-robin over
 // the CTAs so that every SM issues REDs: scattered REDs leave an SM at ~0.66 lanes/clock whatever the occupancy
 // (tools/microbench_red.cu: 190 G/s chip-wide), which is the bound of the counting phase.
@@ -837,7 +838,6 @@ struct WaveParams {
     uint32_t k;
     int norm_mode;
     int canonical;
-    int out_f32;                  // 0: leave u32 counts, 1: convert rows to f32 (normalised or not) in place
 };
 
 // zero rows [s0, s1): thread `t` of `nt`
@@ -873,31 +873,41 @@ __device__ __forceinline__ float4 wave_cvt4(const WaveParams &p, uint4 c, unsign
     return o;
 }
 
-// counts -> f32 in place for rows [s0, s1): thread `t` of `nt`, 2 independent 16-byte loads in flight per thread
+// counts -> f32 in place for rows [s0, s1): thread `t` of `nt`, 2 independent 16-byte loads in flight per thread.
+// The row of a vector (for its total) is tracked incrementally: one 64-bit division per thread, not per vector.
 __device__ __forceinline__ void wave_finalize_rows(const WaveParams &p, uint64_t s0, uint64_t s1, uint64_t t, uint64_t nt) {
-    if (s0 >= s1 || !p.out_f32) return;
+    if (s0 >= s1) return;
     constexpr int U = 2;
-    const uint64_t nvec = (s1 - s0) * p.dim / 4;
+    const uint64_t vpr = p.dim / 4;                 // vectors per row (dim % 4 == 0 on this path)
+    const uint64_t nvec = (s1 - s0) * vpr;
+    const uint64_t dq = nt / vpr, dr = nt % vpr;    // one stride of nt vectors = dq rows + dr vectors
+    uint64_t row = t / vpr, col = t % vpr;          // of vector i0
     uint4 *buf = reinterpret_cast<uint4 *>(p.rows + s0 * p.dim);
     for (uint64_t i0 = t; i0 < nvec; i0 += U * nt) {
         uint4 c[U];
+        unsigned long long tot[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint64_t i = i0 + (uint64_t)u * nt;
-            if (i < nvec) c[u] = __ldcg(buf + i);
+            if (i < nvec) {
+                c[u] = __ldcg(buf + i);
+                tot[u] = __ldcg(p.totals + s0 + row);
+            }
+            row += dq;
+            col += dr;
+            if (col >= vpr) { col -= vpr; ++row; }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint64_t i = i0 + (uint64_t)u * nt;
-            if (i < nvec)
-                reinterpret_cast<float4 *>(buf)[i] = wave_cvt4(p, c[u], __ldcg(p.totals + s0 + (i * 4) / p.dim));
+            if (i < nvec) reinterpret_cast<float4 *>(buf)[i] = wave_cvt4(p, c[u], tot[u]);
         }
     }
 }
 
 // RANK: 0 raw codes, 1 rank through the L2-resident table, 2 rank computed from shared-memory tables (one
 // look-up + RED per k-mer through L2 halves to the RED alone; the tables fit up to k = 10).
-template <int RANK>
+template <int RANK, bool F32>
 __global__ void __launch_bounds__(1024) wave_kernel(const WaveParams p) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -1023,13 +1033,17 @@ __global__ void __launch_bounds__(1024) wave_kernel(const WaveParams p) {
         for (uint64_t item = slot; item < nitems; item += nslots) {
             do_item(w, (uint32_t)item);
         }
-        // warps without an item start here at once, so the zeroing overlaps the REDs of the others; the zeroed
+        // f32: normalise the wave in place as soon as all its REDs have landed (a second barrier per wave is cheaper
+        // than keeping a third wave in L2 until the next iteration: 6.4 ms -> see DESIGN.md §4.3)
+        if constexpr (F32) {
+            grid.sync();
+            wave_finalize_rows(p, wave_lo(w), wave_lo(w + 1), gt, gnt);
+        }
+        // u32: warps without an item start here at once, so the zeroing overlaps the REDs of the others; the zeroed
         // wave only has to stay in L2 from now on, which is why a wave can be as large as a third of L2
         wave_zero_rows(p, wave_lo(w + 1), wave_lo(w + 2), gt, gnt);
-        if (w > 0) wave_finalize_rows(p, wave_lo(w - 1), wave_lo(w), gt, gnt);
         grid.sync();
     }
-    if (nwaves > 0) wave_finalize_rows(p, wave_lo(nwaves - 1), p.n, gt, gnt);
 }
 
 // ================================================================================================
