@@ -213,6 +213,17 @@ def test_global_path_many_waves(k, mins, persistent):
         check(k, bases, offsets, mins=mins, norm_mode=NORM_CLI, dtype=np.float64, what=f"k{k} f64", **opts)
 
 
+def test_global_path_more_items_than_warps():
+    """One 3 Mbp contig between short ones at k = 9: a wave holds more 512-base steps than the grid has warps, so
+    warps loop over several items, and the step table spans empty and long rows."""
+    rng = np.random.default_rng(77)
+    lengths = np.r_[[700, 0], [3_000_000], rng.integers(5, 3000, size=6)]
+    bases, offsets = random_batch(rng, lengths, noise=0.0005, n_runs=0.05)
+    check(9, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what="k9 long contig u32")
+    check(9, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, what="k9 long contig f32")
+    check(8, bases, offsets, mins=False, norm_mode=NORM_COUNTS, dtype=np.uint32, what="raw k8 long contig u32")
+
+
 @pytest.mark.parametrize("k", [3, 5, 7])
 def test_forced_global_path_matches(k):
     rng = np.random.default_rng(400 + k)

@@ -24,7 +24,8 @@ def _valid_windows_torch(bases, n, L, k):
     return (inwin == 0).sum(dim=1)
 
 
-@pytest.mark.parametrize("workload,scale", [("reads150_k5", 0.2), ("reads10k_k7", 0.02), ("reads10k_k8", 0.05)])
+@pytest.mark.parametrize("workload,scale", [("reads150_k5", 0.2), ("reads10k_k7", 0.02), ("reads10k_k8", 0.05),
+                                            ("reads100k_k10", 0.05)])
 def test_baseline_shapes_by_properties(workload, scale):
     import torch
     import bench
@@ -61,7 +62,7 @@ def test_baseline_shapes_by_properties(workload, scale):
     assert np.array_equal(a, b) and np.array_equal(a, rows[:m].cpu().numpy())
     # (5) a random sample of rows, bit-exact against the oracle
     rng = np.random.default_rng(1)
-    pick = np.sort(rng.choice(n, size=min(n, 3000 if L <= 1000 else 300), replace=False))
+    pick = np.sort(rng.choice(n, size=min(n, 3000 if L <= 1000 else (300 if L <= 10_000 else 24)), replace=False))
     sb = np.concatenate([bases[int(i) * L:(int(i) + 1) * L].cpu().numpy() for i in pick[:300]])
     so = np.arange(len(pick[:300]) + 1, dtype=np.uint64) * L
     want, _ = O.vectorise_batch(sb, so, k, True, 1)
