@@ -181,6 +181,10 @@ int ktb_comp_oligo_file(const ktb_file_opts *opts, ktb_file_stats *stats /* opti
  * column's k-mer in a vecsize x vecsize square.  Uses in_path, out_path, k, norm, device of `opts`. */
 int ktb_comp_cgr_file(const ktb_file_opts *opts, int vecsize, ktb_file_stats *stats /* optional */);
 
+/* The file-level drivers keep their pinned / device buffer sets (at most ~0.5 GB) for the next call on the same
+ * device; this frees them. */
+void ktb_release_cached_buffers(void);
+
 /* Loads a whole FASTA/FASTQ(.gz) file into packed buffers (malloc'ed; release with ktb_free).
  * sniff != 0: format from the first byte, else from the extension. */
 int ktb_fastx_load(const char *path, int sniff, uint8_t **bases, uint64_t **offsets, uint64_t *n);

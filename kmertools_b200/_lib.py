@@ -61,6 +61,7 @@ SYMBOLS = {
     "ktb_host_free": (None, [_VP]),
     "ktb_comp_oligo_file": (_I, [C.POINTER(FileOpts), C.POINTER(FileStats)]),
     "ktb_comp_cgr_file": (_I, [C.POINTER(FileOpts), _I, C.POINTER(FileStats)]),
+    "ktb_release_cached_buffers": (None, []),
     "ktb_fastx_load": (_I, [C.c_char_p, _I, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_U64)]),
     "ktb_free": (None, [_VP]),
     "ktb_debug_format6": (_I, [C.c_double, C.c_char_p]),

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -82,6 +83,55 @@ struct Set {
         if (stream) cudaStreamDestroy(stream);
     }
 };
+
+// The two buffer sets of the last run are kept for the next one on the same device: page-locking costs ~0.5 ms
+// per MB (several times that right after a large pinned region was released), which was half of a warm 1 GB run.
+// One cached pair per process, handed to one caller at a time; never destroyed at exit (the CUDA runtime may be
+// gone by then), ktb_release_cached_buffers() frees it on request.
+struct SetPair {
+    Set sets[2];
+    int device = -1;
+};
+std::mutex g_pool_mutex;
+SetPair *g_pool = nullptr;
+
+SetPair *acquire_sets(int device) {
+    SetPair *sp = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        if (g_pool && g_pool->device == device) {
+            sp = g_pool;
+            g_pool = nullptr;
+        }
+    }
+    if (!sp) {
+        sp = new SetPair();
+        sp->device = device;
+    }
+    for (auto &s : sp->sets) {
+        s.n = s.nbases = s.out_bytes = 0;
+        s.pending = false;
+        if ((!s.stream && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) ||
+            (!s.kernels_done && cudaEventCreateWithFlags(&s.kernels_done, cudaEventDisableTiming) != cudaSuccess)) {
+            delete sp;
+            return nullptr;
+        }
+    }
+    return sp;
+}
+
+void release_sets(SetPair *sp) {
+    if (!sp) return;
+    for (auto &s : sp->sets)
+        if (s.stream) cudaStreamSynchronize(s.stream);   // an error path may leave copies in flight
+    SetPair *old = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        old = g_pool;
+        g_pool = sp;
+    }
+    delete old;
+}
 
 // u32 counts -> "c0<d>c1<d>...\n" (format!("{}", f64) prints integral values without ".0", oligo.rs:138)
 size_t format_counts_rows(const uint32_t *counts, uint64_t n, uint32_t dim, char delim, std::vector<char> *out) {
@@ -252,7 +302,8 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
     const bool gpu_text = norm && !cgr;          // fixed-width rows are formatted on the GPU
     const size_t out_per_row = gpu_text ? dim * 9 : ((cgr && norm) ? dim * 8 : dim * 4);
     // batches of 64 MB of output / 32 MB of bases: page-locking the two buffer sets is the fixed cost of a run
-    // (~0.4 ms per MB; 1 GB of text: 752 ms -> 370 ms), and a batch this size already hides every launch latency.
+    // (~0.5 ms per MB; 1 GB of text: 752 ms -> 370 ms, 293 ms with the cached sets), and a batch this size already
+    // hides every launch latency.
     // Measured and not kept: 8 threads of pwrite per batch (buffered writes to one file serialise in the kernel).
     const size_t OUT_CAP = 64u << 20;
     const size_t max_records = std::max<size_t>(1, std::min<size_t>(OUT_CAP / out_per_row, 4u << 20));
@@ -266,11 +317,10 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
         }
     }
 
-    Set sets[2];
-    for (auto &s : sets)
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.kernels_done, cudaEventDisableTiming) != cudaSuccess)
-            return ktb_internal_fail(KTB_ERR_CUDA, "cudaStreamCreate failed");
+    SetPair *pair = acquire_sets(o->device);
+    if (!pair) return ktb_internal_fail(KTB_ERR_CUDA, "cudaStreamCreate failed");
+    struct PairGuard { SetPair *p; ~PairGuard() { release_sets(p); } } pair_guard{pair};
+    Set *sets = pair->sets;
     cudaEvent_t prev_kernels_done = nullptr;   // the handle's work counters / scratch are shared: kernels of
                                                // consecutive batches are chained, copies still overlap
     std::vector<char> text;
@@ -303,12 +353,16 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
     };
 
     std::vector<uint64_t> offs;
+    double alloc_ms = 0;   // page-locking / device allocation of the buffer sets (first two batches)
+    const double t_loop = now_ms();
     int b = 0;
     for (;;) {
         Set &s = sets[b & 1];
         if (int rc = finish(s)) return rc;   // this set's previous batch (b-2) must be written first
-        const double tp0 = now_ms();
+        const double ta0 = now_ms();
         if (!s.h_bases.ensure(bases_cap)) return ktb_internal_fail(KTB_ERR_NOMEM, "pinned allocation failed");
+        const double tp0 = now_ms();
+        alloc_ms += tp0 - ta0;
         offs.assign(1, 0);
         size_t used = 0;
         long got = 0;
@@ -330,12 +384,14 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
         st.records += n;
         st.bases += used;
         // ---- enqueue H2D, kernels, D2H
+        const double ta1 = now_ms();
         if (!s.h_offsets.ensure((n + 1) * 8)) return ktb_internal_fail(KTB_ERR_NOMEM, "pinned allocation failed");
         memcpy(s.h_offsets.p, offs.data(), (n + 1) * 8);
         s.out_bytes = n * out_per_row;
         if (!s.h_out.ensure(s.out_bytes) || !s.d_bases.ensure(used + 64) || !s.d_offsets.ensure((n + 1) * 8) ||
             !s.d_counts.ensure(n * dim * 8) || !s.d_totals.ensure(n * 8) || (gpu_text && !s.d_text.ensure(n * dim * 9)))
             return ktb_internal_fail(KTB_ERR_NOMEM, "buffer allocation failed");
+        alloc_ms += now_ms() - ta1;
         cudaMemcpyAsync(s.d_bases.p, s.h_bases.p, used, cudaMemcpyHostToDevice, s.stream);
         cudaMemcpyAsync(s.d_offsets.p, s.h_offsets.p, (n + 1) * 8, cudaMemcpyHostToDevice, s.stream);
         const uint64_t l0 = ktb_internal_launches(h);
@@ -374,11 +430,28 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
     if (fflush(fo) != 0) return ktb_internal_fail(KTB_ERR_IO, "flush failed");
     st.launches = launches;
     st.total_ms = now_ms() - t_start;
+    if (getenv("KTB_FILE_TRACE"))
+        fprintf(stderr, "[ktb file] setup %.1f ms (handle, output file, streams), buffers %.1f ms, parse %.1f ms, gpu wait %.1f ms, "
+                        "write %.1f ms, total %.1f ms\n", t_loop - t_start, alloc_ms, st.parse_ms, st.gpu_wait_ms, st.write_ms,
+                st.total_ms);
     if (stats) *stats = st;
     return KTB_OK;
 }
 
 int ktb_comp_oligo_file(const ktb_file_opts *o, ktb_file_stats *stats) { return run_file(o, stats, 0); }
+
+void ktb_release_cached_buffers(void) {
+    SetPair *old = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        old = g_pool;
+        g_pool = nullptr;
+    }
+    if (old) {
+        cudaSetDevice(old->device);
+        delete old;
+    }
+}
 
 int ktb_comp_cgr_file(const ktb_file_opts *o, int vecsize, ktb_file_stats *stats) {
     if (vecsize < 1) return ktb_internal_fail(KTB_ERR_ARG, "vecsize must be positive");

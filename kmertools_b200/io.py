@@ -60,3 +60,8 @@ def format6(q: float) -> str:
     buf = C.create_string_buffer(9)
     _lib.check(_lib.load().ktb_debug_format6(float(q), buf))
     return buf.raw[:8].decode()
+
+
+def release_cached_buffers() -> None:
+    """Free the pinned / device buffer sets comp_oligo and comp_cgr keep between calls."""
+    _lib.load().ktb_release_cached_buffers()
