@@ -224,6 +224,18 @@ def test_global_path_more_items_than_warps():
     check(8, bases, offsets, mins=False, norm_mode=NORM_COUNTS, dtype=np.uint32, what="raw k8 long contig u32")
 
 
+def test_global_path_degenerate_batches():
+    """Nothing to count (every sequence shorter than k) and the largest supported k (one 33.5 MB row per wave)."""
+    for lengths in ([0, 0, 0], [8, 0, 3]):
+        bases, offsets = random_batch(np.random.default_rng(3), lengths)
+        check(9, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what="k9 nothing to count")
+        check(9, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, what="k9 nothing to count f32")
+    rng = np.random.default_rng(12)
+    bases, offsets = random_batch(rng, [5000, 11, 12, 40000], noise=0.002)
+    check(12, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what="k12 u32")
+    check(12, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, what="k12 f32")
+
+
 @pytest.mark.parametrize("k", [3, 5, 7])
 def test_forced_global_path_matches(k):
     rng = np.random.default_rng(400 + k)
