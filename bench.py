@@ -34,6 +34,14 @@ WORKLOADS = {
     # name: (n, length spec, k, canonical, out dtype, norm)
     "reads150_k5": dict(n=10_000_000, length=150, k=5, dtype="f32", norm=1, seed=20250001,
                         desc="10M x 150bp short reads, k=5 canonical f32 normalised (BASELINE configs[1])"),
+    "reads150_k3": dict(n=10_000_000, length=150, k=3, dtype="f32", norm=1, seed=20250001,
+                        desc="10M x 150bp short reads, k=3 canonical f32 normalised (the CLI's default k; probe, not a BASELINE config)"),
+    "reads150_k4": dict(n=10_000_000, length=150, k=4, dtype="f32", norm=1, seed=20250001,
+                        desc="10M x 150bp short reads, k=4 canonical f32 normalised (probe, not a BASELINE config)"),
+    "reads150_k6": dict(n=2_000_000, length=150, k=6, dtype="f32", norm=1, seed=20250001,
+                        desc="2M x 150bp short reads, k=6 canonical f32 normalised (probe, not a BASELINE config)"),
+    "reads150_k7": dict(n=500_000, length=150, k=7, dtype="f32", norm=1, seed=20250001,
+                        desc="500k x 150bp short reads, k=7 canonical f32 normalised (probe, not a BASELINE config)"),
     "reads10k_k7": dict(n=1_000_000, length=10_000, k=7, dtype="f32", norm=1, seed=20250002,
                         desc="1M x 10kbp long reads, k=7 canonical f32 normalised (BASELINE configs[2])"),
     "reads10k_k6": dict(n=1_000_000, length=10_000, k=6, dtype="f32", norm=1, seed=20250002,
