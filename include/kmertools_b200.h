@@ -133,6 +133,7 @@ int ktb_oligo_last_stats(const ktb_oligo *h, ktb_stats *out);
  *   "chunk_bytes"        target bytes of output per pipeline chunk in the host entry point
  *   "force_path"         0 auto, 1 flat-decomposition global-atomic kernel only, 2 no short-read kernel
  *   "seq_threads"        CTA size of the CTA-per-sequence kernel (0 = heuristic)
+ *   "seq_grab"           sequences a CTA of that kernel takes per trip to the work counter (0 = heuristic)
  *   "dense_odd"          1 (default): dense middle-base histogram for k = 7, 0: code-space histogram
  *   "packed16"           1: packed 16-bit code-space histogram for k = 8 (default 0: rank-space histogram)
  *   "wave_persistent"    1 (default): histograms larger than shared memory (k >= 9, raw k >= 8) are counted by one

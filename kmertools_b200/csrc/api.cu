@@ -118,6 +118,7 @@ struct ktb_oligo {
     int short_variant = 0;
     int short_warps = 0;  // 0 = auto
     int seq_threads = 0;  // 0 = auto (256)
+    int seq_grab = 0;     // work items per atomic in seq_kernel (0 = from the mean sequence length)
     int dense_odd = 1;    // use seq_kernel mode 4 where it applies
     int even_rank = 1;    // use seq_kernel mode 7 where it applies
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
@@ -221,7 +222,12 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     const uint64_t nitems = ((p.n + p.group_size - 1) / p.group_size) * p.group_size;   // one sequence per item
     if (grid > nitems) grid = nitems;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, threads, smem, st>>>(p);
+    // short sequences: several work items per trip to the (same-address) work counter — one atomic per
+    // 150-base read capped the GPU at ~330 M reads/s; long sequences keep one item per trip for the tail
+    SeqParams q = p;
+    q.grab = h->seq_grab > 0 ? (uint32_t)h->seq_grab
+                             : (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(16, 4096 / std::max<uint64_t>(mean_len, 1)));
+    kern<<<(unsigned)grid, threads, smem, st>>>(q);
     CU(cudaGetLastError());
     h->stats.launches++;
     return KTB_OK;
@@ -740,6 +746,9 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->global_steps_per_warp = (int)value;
     } else if (!strcmp(key, "wave_persistent")) {
         h->wave_persistent = value != 0;
+    } else if (!strcmp(key, "seq_grab")) {
+        if (value < 0 || value > 1024) return fail(KTB_ERR_ARG, "seq_grab must be in 0..1024");
+        h->seq_grab = (int)value;
     } else if (!strcmp(key, "wave_smem_rank")) {
         h->wave_smem_rank = value != 0;
     } else if (!strcmp(key, "wave_budget_bytes")) {

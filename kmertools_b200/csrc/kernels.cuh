@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(256) short_kernel(const ShortParams p) {
 // seq_kernel — CTA per sequence, shared-memory atomics
 // ================================================================================================
 struct SeqParams {
+    uint32_t grab = 1;            // consecutive work items taken per atomic on `counter`
     const uint8_t *bases;        // 16-byte aligned
     const uint64_t *offsets;
     uint64_t n;
@@ -627,12 +628,16 @@ seq_kernel(const SeqParams p) {
     uint8_t *hbytes = reinterpret_cast<uint8_t *>(hist);
     const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
 
+    // p.grab consecutive items per trip to the work counter: one same-address atomic per 150-base read capped the
+    // whole GPU at ~330 M reads/s; long sequences keep grab = 1 for the tail balance
+    const unsigned long long grab = p.grab ? p.grab : 1u;
     for (;;) {
-        if (tid == 0) s_group = atomicAdd(p.counter, 1ULL);
+        if (tid == 0) s_group = atomicAdd(p.counter, grab);
         __syncthreads();
-        const unsigned long long item = s_group;
+        const unsigned long long item0 = s_group;
         __syncthreads();  // everyone has read s_group before tid 0 overwrites it next round
-        if (item >= nitems) break;
+        if (item0 >= nitems) break;
+      for (unsigned long long item = item0; item < min(item0 + grab, (unsigned long long)nitems); ++item) {
         uint64_t i0;
         uint32_t nseq, tile = 0, tiles = 1;
         if constexpr (HIST_MODE == 3) {  // work item = (sequence of the wave, tile of that sequence)
@@ -801,6 +806,7 @@ seq_kernel(const SeqParams p) {
                 seq_write_row<OUT, HIST_MODE, NORM, false>(hist, row, p, dF, rinv, dD);
             __syncthreads();
         }
+      }
     }
 }
 
