@@ -212,7 +212,8 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     // per CTA (less barrier / priming overhead, occupancy is not the limit); long contigs and the big
     // histograms want 8 warps.
     const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
-    const int auto_threads = ((mean_len <= 16384 && (smem <= 16 * 1024 || hist_mode == 5)) ? 128 : 256);
+    const int auto_threads = (mean_len <= 512 && smem <= 16 * 1024 && hist_mode != 5) ? 64   // one step per read: k = 6 short reads +7 %
+                             : ((mean_len <= 16384 && (smem <= 16 * 1024 || hist_mode == 5)) ? 128 : 256);
     int threads = h->seq_threads > 0 ? h->seq_threads : auto_threads;
     if (hist_mode == 5 && threads > 256) threads = 256;
     if (hist_mode != 2 && hist_mode != 5 && hist_mode != 7 && threads > KTB_SEQ_MAXTHREADS) threads = KTB_SEQ_MAXTHREADS;
