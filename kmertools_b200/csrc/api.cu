@@ -124,6 +124,7 @@ struct ktb_oligo {
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
     int global_steps_per_warp = 1;
     int wave_persistent = 1;                 // global-atomic path as one cooperative launch (u32 / f32 output)
+    bool coop_launch = false;                // device attribute, read at create
     int64_t wave_budget_bytes = 96ll << 20;  // L2 budget of the cooperative kernel, a wave is a third of it
     int wave_smem_rank = 1;                  // rank from shared-memory tables when they fit (k <= 10)
     int64_t global_wave_bytes = 64ll << 20;  // rows zeroed + counted together in the global-atomic path (fits L2)
@@ -350,7 +351,7 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
             h->stats.launches++;
         }
         if (int rc = finalize(counts, 0, n)) return rc;
-    } else if (h->wave_persistent && OUT != OUT_F64 && n > 0) {
+    } else if (h->wave_persistent && h->coop_launch && OUT != OUT_F64 && n > 0) {
         // One persistent cooperative launch: the wave loop (zero next rows / count / normalise previous rows)
         // runs on the device with a grid barrier per wave instead of three launches per wave.
         WaveParams wp{};
@@ -547,6 +548,7 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
         return bail(fail(KTB_ERR_CUDA, "cudaGetDeviceProperties failed"));
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->coop_launch = prop.cooperativeLaunch != 0;   // wave_kernel needs co-resident CTAs; else the multi-launch variant
 
 #define CUB(call)                                                                                  \
     do {                                                                                           \
