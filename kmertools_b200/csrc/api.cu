@@ -6,6 +6,7 @@
 // a CUDA device every compute entry point returns KTB_ERR_NODEVICE.
 #include "../../include/kmertools_b200.h"
 #include "kernels.cuh"
+#include "long_kernel.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -103,6 +104,8 @@ struct ktb_oligo {
     uint32_t *d_wave_tab = nullptr;        // canonical-code bitmap + u32 pair prefixes for wave_kernel<2>
     uint32_t wave_tab_words = 0;
     uint64_t mb_entries = 0;               // histogram words mode 4 needs (dense index + skew)
+    uint32_t *d_k7_sched = nullptr;        // k = 7: conflict-free write-out schedule of long_kernel MODE_K7
+    uint32_t *d_fwd_sched = nullptr;       // 3 <= k <= 6: (offset of c | offset of rc(c) << 16) per rank, long_kernel MODE_FWD
     uint32_t *d_short_tab_canon = nullptr; // [4^k] (k <= 5): (word byte offset << 22) | 8*(bin&3)
     uint32_t *d_short_tab_raw = nullptr;
     unsigned long long *d_counters = nullptr;  // [4]
@@ -121,6 +124,9 @@ struct ktb_oligo {
     int seq_grab = 0;     // work items per atomic in seq_kernel (0 = from the mean sequence length)
     int dense_odd = 1;    // use seq_kernel mode 4 where it applies
     int even_rank = 1;    // use seq_kernel mode 7 where it applies
+    int k7_mid = 1;       // long_kernel MODE_K7 (k = 7 canonical, u32 / f32 rows)
+    int fwd_fold = 1;     // long_kernel MODE_FWD (3 <= k <= 6 canonical, long sequences, u32 / f32 rows)
+    int64_t fwd_min_len = 1024;   // mean sequence length from which MODE_FWD replaces seq_kernel mode 1
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
     int global_steps_per_warp = 1;
     int wave_persistent = 1;                 // global-atomic path as one cooperative launch (u32 / f32 output)
@@ -235,6 +241,98 @@ int launch_seq(ktb_oligo *h, const SeqParams &p, int hist_mode, cudaStream_t st)
     return KTB_OK;
 }
 
+
+// Splits the (bin word, rank) pairs of a row into groups of 32 whose source banks (word % 32) are all distinct and
+// whose destination banks (rank % 32) are all distinct, so that a warp moves a group between two shared-memory
+// arrays without a bank conflict on either side.  The pairs are the edges of a bipartite multigraph (source bank,
+// destination bank) that is d-regular with d = n / 32; when d is a power of two it is split into two d/2-regular
+// halves by alternating along closed trails (every vertex keeps half of its edges on each side) until d = 1, i.e.
+// perfect matchings.  `word_of_rank[j]` must be a bijection onto [0, n); returns the ranks group after group, lane
+// l of a group holding the pair whose rank has bank l.  Empty on failure (n / 32 not a power of two).
+std::vector<uint32_t> conflict_free_groups(const std::vector<uint32_t> &word_of_rank) {
+    const uint32_t n = (uint32_t)word_of_rank.size();
+    if (n == 0 || n % 32) return {};
+    const uint32_t deg = n / 32;
+    if (deg & (deg - 1)) return {};
+    std::vector<std::vector<uint32_t>> parts(1), next;
+    parts[0].resize(n);
+    for (uint32_t j = 0; j < n; ++j) parts[0][j] = j;
+    for (uint32_t d = deg; d > 1; d >>= 1) {
+        next.clear();
+        for (const auto &edges : parts) {
+            // adjacency: vertices 0..31 = source banks, 32..63 = destination banks
+            std::vector<uint32_t> adj[64];
+            for (uint32_t e = 0; e < edges.size(); ++e) {
+                adj[word_of_rank[edges[e]] & 31].push_back(e);
+                adj[32 + (edges[e] & 31)].push_back(e);
+            }
+            std::vector<uint8_t> used(edges.size(), 0);
+            size_t ptr[64] = {};
+            std::vector<uint32_t> half[2];
+            for (int v0 = 0; v0 < 64; ++v0) {
+                int cur = v0, side = 0;
+                for (;;) {
+                    while (ptr[cur] < adj[cur].size() && used[adj[cur][ptr[cur]]]) ++ptr[cur];
+                    if (ptr[cur] == adj[cur].size()) break;   // only possible back at v0: every degree is even
+                    const uint32_t e = adj[cur][ptr[cur]];
+                    used[e] = 1;
+                    half[side].push_back(edges[e]);
+                    side ^= 1;
+                    const int a = (int)(word_of_rank[edges[e]] & 31), b = 32 + (int)(edges[e] & 31);
+                    cur = (cur == a) ? b : a;
+                }
+            }
+            if (half[0].size() != half[1].size()) return {};
+            next.push_back(std::move(half[0]));
+            next.push_back(std::move(half[1]));
+        }
+        parts.swap(next);
+    }
+    std::vector<uint32_t> order(n);
+    for (size_t g = 0; g < parts.size(); ++g) {
+        if (parts[g].size() != 32) return {};
+        uint32_t seen_s = 0, seen_d = 0;
+        for (uint32_t j : parts[g]) {
+            seen_s |= 1u << (word_of_rank[j] & 31);
+            seen_d |= 1u << (j & 31);
+            order[g * 32 + (j & 31)] = j;
+        }
+        if (seen_s != 0xFFFFFFFFu || seen_d != 0xFFFFFFFFu) return {};
+    }
+    return order;
+}
+
+template <int OUT>
+int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
+    if constexpr (OUT == OUT_F64) {
+        (void)h; (void)p; (void)mode; (void)st;
+        return fail(KTB_ERR_ARG, "long_kernel has no f64 instance");
+    } else {
+        const bool nrm = p.norm_mode != NORM_COUNTS;
+        void (*kern)(const LongParams) = nullptr;
+        if (mode == MODE_K7) kern = nrm ? long_kernel<OUT, true, MODE_K7> : long_kernel<OUT, false, MODE_K7>;
+        else kern = nrm ? long_kernel<OUT, true, MODE_FWD> : long_kernel<OUT, false, MODE_FWD>;
+        const size_t smem = ((((size_t)p.hist_words + 31) & ~(size_t)31) + p.dim) * 4;
+        if (int rc = set_smem(kern, smem)) return rc;
+        int per_sm = 1;
+        const int threads = LONG_WARPS * 32;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+        if (per_sm < 1) per_sm = 1;
+        uint64_t grid = (uint64_t)h->sm_count * per_sm;
+        const uint64_t nitems = ((p.n + p.group_size - 1) / p.group_size) * p.group_size;
+        if (grid > nitems) grid = nitems;
+        if (grid < 1) grid = 1;
+        const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
+        LongParams q = p;
+        q.grab = h->seq_grab > 0 ? (uint32_t)h->seq_grab
+                                 : (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(16, 4096 / std::max<uint64_t>(mean_len, 1)));
+        kern<<<(unsigned)grid, threads, smem, st>>>(q);
+        CU(cudaGetLastError());
+        h->stats.launches++;
+        return KTB_OK;
+    }
+}
+
 template <int OUT>
 int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n,
                uint64_t total_bases, int canonical, int norm_mode, void *d_out, uint64_t *d_totals,
@@ -283,6 +381,27 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
             sp.max_len = sc.max_len;
             sp.norm_mode = norm_mode; sp.canonical = canonical;
             if (int rc = launch_short<OUT>(h, sp, sc, st)) return rc;
+        }
+        // second-generation CTA-per-sequence kernel (long_kernel.cuh) where it applies
+        const uint64_t mean_len = total_bases / std::max<uint64_t>(n, 1);
+        int long_mode = -1;
+        if (OUT != OUT_F64 && canonical && h->force_path != 3) {
+            if (h->k == 7 && h->k7_mid && h->d_k7_sched) long_mode = MODE_K7;
+            else if (h->d_fwd_sched && h->fwd_fold && (int64_t)mean_len >= h->fwd_min_len) long_mode = MODE_FWD;
+        }
+        if (long_mode >= 0) {
+            LongParams lp{};
+            lp.bases = d_bases; lp.offsets = d_offsets; lp.n = n; lp.total_bases = total_bases;
+            lp.out = d_out; lp.totals = d_totals;
+            lp.sched = long_mode == MODE_K7 ? h->d_k7_sched : h->d_fwd_sched;
+            lp.counter = h->d_counters + 1;
+            lp.list = sc.ok ? (const uint32_t *)h->ws_list.p : nullptr;
+            lp.list_count = sc.ok ? h->d_counters + 2 : nullptr;
+            lp.group_size = SHORT_G;
+            lp.k = h->k; lp.dim = (uint32_t)dim;
+            lp.hist_words = long_mode == MODE_K7 ? K7_BINS : (uint32_t)h->ncodes + 4;
+            lp.norm_mode = norm_mode; lp.canonical = canonical;
+            return launch_long<OUT>(h, lp, long_mode, st);
         }
         SeqParams qp{};
         qp.bases = d_bases; qp.offsets = d_offsets; qp.n = n; qp.total_bases = total_bases;
@@ -613,6 +732,35 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
             CUB(cudaMemcpy(h->d_mb_perm, mbp.data(), mbp.size() * 4, cudaMemcpyHostToDevice));
         }
     }
+    if (k == 7) {   // long_kernel MODE_K7: bin of a class = [b3 b4 b5 b6 | b0 b1 b2] of the strand whose middle base is A/C
+        std::vector<uint32_t> word(h->dim_canon);
+        for (uint64_t j = 0; j < h->dim_canon; ++j) {
+            uint32_t sgl = h->canon_of_rank[j];
+            if (((sgl >> 6) & 3u) >= 2u) sgl = (uint32_t)rev_comp(sgl, 7);
+            word[j] = ((sgl & 0xFFu) << 6) | ((sgl >> 8) & 0x3Fu);
+        }
+        const std::vector<uint32_t> order = conflict_free_groups(word);
+        if (!order.empty()) {
+            // warp iteration w, lane l, element q  <-  group 4w + q, lane l   (one 128-bit load per lane and iteration)
+            std::vector<uint32_t> sched(h->dim_canon);
+            for (uint64_t g = 0; g < h->dim_canon / 32; ++g)
+                for (uint32_t l = 0; l < 32; ++l) {
+                    const uint32_t j = order[g * 32 + l];
+                    sched[((g >> 2) * 32 + l) * 4 + (g & 3)] = (word[j] * 4u) | ((j * 4u) << 16);
+                }
+            CUB(cudaMalloc(&h->d_k7_sched, sched.size() * 4));
+            CUB(cudaMemcpy(h->d_k7_sched, sched.data(), sched.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    if (k >= 3 && k <= 6 && (h->dim_canon % 4) == 0) {   // long_kernel MODE_FWD: fold table, rank -> (c, rc(c))
+        std::vector<uint32_t> sched(h->dim_canon);
+        for (uint64_t j = 0; j < h->dim_canon; ++j) {
+            const uint32_t c = h->canon_of_rank[j], r = (uint32_t)rev_comp(c, k);
+            sched[j] = (c * 4u) | (((r == c) ? (uint32_t)h->ncodes : r) * 4u) << 16;
+        }
+        CUB(cudaMalloc(&h->d_fwd_sched, sched.size() * 4));
+        CUB(cudaMemcpy(h->d_fwd_sched, sched.data(), sched.size() * 4, cudaMemcpyHostToDevice));
+    }
     {   // wave_kernel<2>: rank(c) = prefix[w / 2] + popc(bits below c) for canonical c, tables in shared memory
         const uint64_t words = h->ncodes / 32;
         const uint64_t bytes = words * 4 + (words / 2) * 4;
@@ -689,6 +837,8 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     if (h->d_mb_perm) cudaFree(h->d_mb_perm);
     if (h->d_even_tab) cudaFree(h->d_even_tab);
     if (h->d_wave_tab) cudaFree(h->d_wave_tab);
+    if (h->d_k7_sched) cudaFree(h->d_k7_sched);
+    if (h->d_fwd_sched) cudaFree(h->d_fwd_sched);
     if (h->d_short_tab_canon) cudaFree(h->d_short_tab_canon);
     if (h->d_short_tab_raw) cudaFree(h->d_short_tab_raw);
     if (h->d_counters) cudaFree(h->d_counters);
@@ -739,6 +889,12 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->short_variant = (int)value;
     } else if (!strcmp(key, "short_warps")) {
         h->short_warps = (int)value;
+    } else if (!strcmp(key, "k7_mid")) {
+        h->k7_mid = (int)value;
+    } else if (!strcmp(key, "fwd_fold")) {
+        h->fwd_fold = (int)value;
+    } else if (!strcmp(key, "fwd_min_len")) {
+        h->fwd_min_len = value;
     } else if (!strcmp(key, "packed16")) {
         h->packed16 = (int)value;
     } else if (!strcmp(key, "even_rank")) {

@@ -1,0 +1,299 @@
+// long_kernel.cuh — CTA-per-sequence kernel for medium / long sequences, second generation (round 2).
+//
+// Same arithmetic as seq_kernel (kernels.cuh; closed form of kmer/src/kmer.rs:80-106 +
+// composition/src/oligo.rs:231-259), with two changes that remove most of the per-k-mer and per-column work:
+//
+//   MODE_K7  (k = 7, canonical).  The two strands of an odd k-mer differ in the top bit of their MIDDLE base
+//            (m vs 3-m), so a 16-bit key whose most significant digit is the middle base orders the strands:
+//                key(s) = [b3 b4 b5 b6 | b0 b1 b2 b3]      (two bytes of the 2-bit packed stream, b3 twice)
+//            min(key(f), key(r)) is the strand whose middle base is A or C, its bit 15 is 0, and after masking
+//            the duplicated b3 it IS the byte offset of a dense 8192-bin u32 histogram (32 KB).  Both bytes of
+//            a key are byte-aligned in one of four phase-shifted views of the packed stream, so TWO keys are
+//            built with one PRMT per strand, canonicalised with one VIMNMX.U16x2 and masked with one LOP3:
+//            ~4 integer instructions per k-mer instead of ~9 (two funnel shifts, two masks, test, select,
+//            shift, multiply-add in seq_kernel mode 4).
+//            Write-out: the bins of consecutive ranks are NOT in consecutive banks in this layout, so the
+//            (bin -> rank) permutation is done through a host-built SCHEDULE: the 8192 (bin, rank) pairs are
+//            split into 256 groups of 32 in which all source banks and all destination banks are distinct
+//            (edge colouring of a 256-regular bipartite multigraph, api.cu), so a warp moves one group with one
+//            conflict-free LDS, one conflict-free re-initialising STS and one conflict-free STS into a 32 KB
+//            row image, which ONE bulk asynchronous copy (cp.async.bulk.global.shared::cta, SASS UBLKCP) then
+//            drains to HBM while the CTA already counts its next sequence.  seq_kernel's gather measured 2.5
+//            wavefronts per LDS/STS and 8192 STGs per row on the LSU.
+//            Bins hold the FLOAT 2^23 + count (initial value 0x4B000000, incremented with integer atomics), so
+//            the count -> float conversion of the normalisation is free.
+//
+//   MODE_FWD (3 <= k <= 6, canonical, long sequences).  Counts the FORWARD code only (4^k bins) and folds the two
+//            strands at write-out, row[rank(c)] = hist[c] + hist[rc(c)] (once per column instead of once per
+//            k-mer): no reverse-complement packing, no second extraction and no min in the inner loop.
+//
+// Both write rows as one bulk copy from shared memory.  f64 output keeps seq_kernel.
+#pragma once
+#include "kernels.cuh"
+
+namespace ktb {
+
+constexpr int MODE_K7 = 0, MODE_FWD = 1;
+constexpr int LONG_WARPS = 8;
+constexpr uint32_t K7_BINS = 8192;
+constexpr uint32_t FLOAT_2P23 = 0x4B000000u;
+
+struct LongParams {
+    const uint8_t *bases;        // 16-byte aligned
+    const uint64_t *offsets;
+    uint64_t n;
+    uint64_t total_bases;
+    void *out;                   // n x dim of 4-byte elements (u32 / f32)
+    uint64_t *totals;            // optional
+    const uint32_t *sched;       // MODE_K7: [dim] (bin byte offset | rank byte offset << 16), group-major (see api.cu)
+                                 // MODE_FWD: [dim] (byte offset of c | byte offset of rc(c) << 16) in rank order
+    unsigned long long *counter; // dynamic work counter (zeroed before launch)
+    const uint32_t *list;        // groups to process (short_kernel's rejects); nullptr = every group
+    const unsigned long long *list_count;
+    uint32_t group_size;
+    uint32_t grab;               // consecutive work items per trip to the counter
+    uint32_t k;
+    uint32_t dim;
+    uint32_t hist_words;         // MODE_K7: 8192; MODE_FWD: 4^k + 4 (the word at 4^k stays zero: rc slot of palindromes)
+    int norm_mode;
+    int canonical;
+};
+
+__device__ __forceinline__ uint32_t smem_u32addr(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+// shared -> global bulk asynchronous copy (TMA engine), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32addr(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all earlier bulk copies of this thread have finished READING shared memory
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (the bulk copy engine)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32-bit window of the 64-bit value (hi:lo) starting at bit S (compile-time, 0..32)
+template <int S>
+__device__ __forceinline__ uint32_t win32(uint32_t lo, uint32_t hi) {
+    if constexpr (S == 0) return lo;
+    else if constexpr (S == 32) return hi;
+    else return __funnelshift_r(lo, hi, S);
+}
+
+// The 16 k = 7 keys of one lane (windows ending at bases 0..15 of the current chunk), as histogram byte
+// offsets.  off[e] belongs to the window that ENDS at base e (validity bit 15 - e of the window mask).
+template <int PHI>
+__device__ __forceinline__ void k7_keys_phase(uint32_t cf, uint32_t cf_prev, uint32_t rc, uint32_t rc_prev,
+                                              uint32_t *off) {
+    // forward strand: F64 = cf_prev:cf, base i (-16..15) at bit 2*(15-i).  View B holds the bytes [b3 b4 b5 b6] of the
+    // windows ending at e = PHI+12, PHI+8, PHI+4, PHI in bytes 0..3; view A the bytes [b0 b1 b2 b3] of the same windows.
+    const uint32_t B = win32<6 - 2 * PHI>(cf, cf_prev);
+    const uint32_t A = win32<12 - 2 * PHI>(cf, cf_prev);
+    // reverse strand: R64 = rc(cf):rc(cf_prev), base i at bit 2*(i+16), complemented.  Byte j of RB / RA belongs to e = PHI+4j.
+    const uint32_t RB = win32<2 * PHI + 20>(rc_prev, rc);
+    const uint32_t RA = win32<2 * PHI + 26>(rc_prev, rc);
+    // pair 0: low half e = PHI+12, high half e = PHI+8;  pair 1: low half e = PHI+4, high half e = PHI
+    const uint32_t f0 = __byte_perm(A, B, 0x5140), r0 = __byte_perm(RA, RB, 0x6273);
+    const uint32_t f1 = __byte_perm(A, B, 0x7362), r1 = __byte_perm(RA, RB, 0x4051);
+    // the strands differ in the top bit of the key (middle base m vs 3-m): the minimum has bit 15 clear
+    const uint32_t k0 = __vminu2(f0, r0) & 0x7FFC7FFCu;
+    const uint32_t k1 = __vminu2(f1, r1) & 0x7FFC7FFCu;
+    off[PHI + 12] = k0 & 0xFFFFu;
+    off[PHI + 8] = k0 >> 16;
+    off[PHI + 4] = k1 & 0xFFFFu;
+    off[PHI] = k1 >> 16;
+}
+
+template <int OUT, bool NORM, int MODE>
+__global__ void __launch_bounds__(LONG_WARPS * 32, MODE == MODE_K7 ? 3 : 4) long_kernel(const LongParams p) {
+    static_assert(OUT == OUT_U32 || OUT == OUT_F32, "f64 rows keep seq_kernel");
+    extern __shared__ __align__(128) uint32_t lsm[];
+    __shared__ unsigned long long s_item;
+    __shared__ uint32_t s_total[2];
+
+    uint32_t *hist = lsm;
+    uint32_t *stage = lsm + ((p.hist_words + 31u) & ~31u);   // row image: dim x 4 bytes, 128-byte aligned
+    uint8_t *hbytes = reinterpret_cast<uint8_t *>(hist);
+    uint8_t *sbytes = reinterpret_cast<uint8_t *>(stage);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t warp = tid >> 5;
+    constexpr uint32_t NW = LONG_WARPS;
+    constexpr uint32_t FULL = 0xffffffffu;
+    // MODE_K7 bins hold the float 2^23 + count (see header)
+    constexpr uint32_t INIT = (MODE == MODE_K7) ? FLOAT_2P23 : 0u;
+
+    const uint64_t ngroups = p.list ? (uint64_t)*p.list_count : (p.n + p.group_size - 1) / p.group_size;
+    const uint64_t nitems = ngroups * p.group_size;
+    if ((uint64_t)blockIdx.x >= nitems) return;
+    for (uint32_t i = tid; i < p.hist_words; i += NW * 32) hist[i] = INIT;
+    if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
+    __syncthreads();
+
+    const uint32_t k = (MODE == MODE_K7) ? 7u : p.k;
+    const uint32_t kmask4 = ((1u << (2 * k)) - 1u) << 2;
+    (void)kmask4;
+    using T = typename OutT<OUT>::type;
+    T *out = reinterpret_cast<T *>(p.out);
+    const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+    const unsigned long long grab = p.grab ? p.grab : 1u;
+    uint32_t it = 0;
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(p.counter, grab);
+        __syncthreads();
+        const unsigned long long item0 = s_item;
+        __syncthreads();
+        if (item0 >= nitems) break;
+        const unsigned long long item1 = min(item0 + grab, (unsigned long long)nitems);
+        for (unsigned long long item = item0; item < item1; ++item) {
+            const uint64_t gi = item / p.group_size;
+            const uint64_t g = p.list ? (uint64_t)p.list[gi] : gi;
+            const uint64_t seq = g * (uint64_t)p.group_size + (item - gi * p.group_size);
+            if (seq >= p.n) continue;   // uniform for the CTA
+            const uint64_t s0 = p.offsets[seq];
+            const uint64_t s1 = p.offsets[seq + 1];
+            uint32_t mine = 0;
+            if (s1 - s0 >= k) {
+                const uint64_t cbase = s0 >> 4;
+                const uint32_t nch = (uint32_t)(((s1 - 1) >> 4) - cbase) + 1u;
+                const uint32_t nsteps = (nch + 31) >> 5;
+                // contiguous runs of whole 32-chunk steps per warp
+                const uint32_t w0 = ((warp * nsteps) / NW) << 5;
+                const uint32_t w1 = min(nch, (((warp + 1) * nsteps) / NW) << 5);
+                const uint32_t head_mask = 0xFFFFu >> (uint32_t)(s0 & 15);
+                const uint32_t tail_mask = ~(0xFFFFu >> ((uint32_t)((s1 - 1) & 15) + 1u)) & 0xFFFFu;
+                if (w0 < w1) {
+                    uint32_t carry_cf = 0, carry_vm = 0;
+                    if (w0 > 0) {   // prime the look-back with the chunk before this warp's range
+                        const uint4 v = load16_guarded(p.bases, (cbase + w0 - 1) << 4, p.total_bases);
+                        decode16(v, carry_cf, carry_vm);
+                        if (w0 == 1) carry_vm &= head_mask;
+                    }
+                    const uint4 *seq_chunks = reinterpret_cast<const uint4 *>(p.bases) + cbase;
+                    const bool near_end = ((cbase + nch) << 4) > p.total_bases;
+                    auto fetch = [&](uint32_t c) -> uint4 {
+                        if (c >= w1) return filler;
+                        if (near_end) return load16_guarded(p.bases, (cbase + c) << 4, p.total_bases);
+                        return __ldg(seq_chunks + c);
+                    };
+                    uint4 vnext = fetch(w0 + lane);
+                    for (uint32_t c0 = w0; c0 < w1; c0 += 32) {
+                        const uint32_t c = c0 + lane;
+                        const uint4 v = vnext;
+                        if (c0 + 32 < w1) vnext = fetch(c + 32);
+                        uint32_t cf, vm;
+                        decode16(v, cf, vm);
+                        if (c >= w1) { vm = 0; cf = (uint32_t)lane * 0x9E3779B1u; }   // idle lanes add 0 at scattered bins
+                        if (c == 0) vm &= head_mask;
+                        if (c == nch - 1) vm &= tail_mask;
+                        uint32_t cf_prev = __shfl_up_sync(FULL, cf, 1);
+                        uint32_t vm_prev = __shfl_up_sync(FULL, vm, 1);
+                        if (lane == 0) { cf_prev = carry_cf; vm_prev = carry_vm; }
+                        carry_cf = __shfl_sync(FULL, cf, 31);
+                        carry_vm = __shfl_sync(FULL, vm, 31);
+                        const uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
+                        mine += __popc(vw);
+                        uint32_t off[16];   // histogram byte offsets; off[e] = window ending at base e
+                        if constexpr (MODE == MODE_K7) {
+                            const uint32_t rc = revcomp_pack(cf), rc_prev = revcomp_pack(cf_prev);
+                            k7_keys_phase<0>(cf, cf_prev, rc, rc_prev, off);
+                            k7_keys_phase<1>(cf, cf_prev, rc, rc_prev, off);
+                            k7_keys_phase<2>(cf, cf_prev, rc, rc_prev, off);
+                            k7_keys_phase<3>(cf, cf_prev, rc, rc_prev, off);
+                        } else {
+                            const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                off[e] = (e < 15) ? ((uint32_t)(F64 >> (2 * (14 - e))) & kmask4) : ((cf << 2) & kmask4);
+                        }
+                        if (__all_sync(FULL, vw == 0xFFFFu)) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), 1u);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)   // branch-free: an invalid window adds 0
+                                atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), (vw >> (15 - e)) & 1u);
+                        }
+                    }
+                }
+            }
+            // ---- total = block sum of `mine`
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) mine += __shfl_xor_sync(FULL, mine, s);
+            if (lane == 0 && mine) atomicAdd(&s_total[it & 1], mine);
+            // the row image is about to be overwritten: the bulk copy of the previous row must have read it
+            if (tid == 0) bulk_wait_read();
+            __syncthreads();
+            const uint32_t total = s_total[it & 1];
+            if (tid == 0) s_total[(it + 1) & 1] = 0;
+            ++it;
+            const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
+            const float dF = (float)dv;
+            const float rinv = __frcp_rn(dF);
+            const double dD = (double)dv;
+            if (tid == 0 && p.totals) p.totals[seq] = total;
+            const bool small = dv < (1ULL << 23);   // counts and divisor exact in f32, magic-constant conversion valid
+
+            // ---- write-out into the row image (normalisation fused), histogram re-initialised on the way
+            if constexpr (MODE == MODE_K7) {
+                const uint4 *sched4 = reinterpret_cast<const uint4 *>(p.sched);
+                const uint32_t niter = p.dim >> 7;   // 128 (bin, rank) pairs per warp iteration
+                const float nK = -8388608.0f * rinv;
+                uint4 en = (warp < niter) ? __ldg(sched4 + warp * 32 + lane) : make_uint4(0, 0, 0, 0);
+                for (uint32_t w = warp; w < niter; w += NW) {
+                    const uint4 e4 = en;
+                    if (w + NW < niter) en = __ldg(sched4 + (w + NW) * 32 + lane);
+                    const uint32_t ee[4] = {e4.x, e4.y, e4.z, e4.w};
+                    uint32_t bits[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t *bin = reinterpret_cast<uint32_t *>(hbytes + (ee[q] & 0xFFFFu));
+                        bits[q] = *bin;
+                        *bin = INIT;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        T val;
+                        if constexpr (OUT == OUT_U32) {
+                            val = bits[q] - INIT;
+                        } else if (small) {
+                            const float F = __uint_as_float(bits[q]);   // 2^23 + count
+                            const float cnt = F - 8388608.0f;
+                            if constexpr (NORM) {
+                                const float q0 = fmaf(F, rinv, nK);        // RN(count * rinv), as quot_f32
+                                const float rem = fmaf(-q0, dF, cnt);
+                                val = fmaf(rem, rinv, q0);
+                            } else {
+                                val = cnt;
+                            }
+                        } else {
+                            const uint32_t cnt = bits[q] - INIT;
+                            val = NORM ? (float)((double)cnt / dD) : (float)cnt;
+                        }
+                        *reinterpret_cast<T *>(sbytes + (ee[q] >> 16)) = val;
+                    }
+                }
+            } else {
+                for (uint32_t j = tid; j < p.dim; j += NW * 32) {
+                    const uint32_t e = __ldg(p.sched + j);
+                    uint32_t *a = reinterpret_cast<uint32_t *>(hbytes + (e & 0xFFFFu));
+                    uint32_t *b = reinterpret_cast<uint32_t *>(hbytes + (e >> 16));
+                    const uint32_t cnt = *a + *b;   // palindromes: b is the always-zero word
+                    *a = 0;
+                    *b = 0;
+                    reinterpret_cast<T *>(stage)[j] = small ? cvt_count<OUT, NORM, true>(cnt, dF, rinv, dD)
+                                                            : cvt_count<OUT, NORM, false>(cnt, dF, rinv, dD);
+                }
+            }
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) bulk_store(out + seq * (uint64_t)p.dim, stage, p.dim * 4u);
+        }
+    }
+    if (tid == 0) bulk_wait_all();
+}
+
+}  // namespace ktb
