@@ -7,6 +7,7 @@
 #include "../../include/kmertools_b200.h"
 #include "kernels.cuh"
 #include "long_kernel.cuh"
+#include "bucket_kernels.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -110,6 +111,7 @@ struct ktb_oligo {
     uint32_t *d_short_tab_raw = nullptr;
     unsigned long long *d_counters = nullptr;  // [4]
     DevBuf ws_totals, ws_counts, ws_list, ws_list2;
+    DevBuf ws_tiles, ws_pool, ws_runs;     // bucket path: tile prefix, sorted index pool, run descriptors
     ChunkSet sets[NBUF];
     cudaStream_t aux[2] = {nullptr, nullptr};   // wave overlap in the global-atomic path
     cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
@@ -124,9 +126,12 @@ struct ktb_oligo {
     int seq_grab = 0;     // work items per atomic in seq_kernel (0 = from the mean sequence length)
     int dense_odd = 1;    // use seq_kernel mode 4 where it applies
     int even_rank = 1;    // use seq_kernel mode 7 where it applies
+    int long_warps = 0;   // warps per CTA of long_kernel: 0 = from the mean sequence length, else 4 or 8
     int k7_mid = 1;       // long_kernel MODE_K7 (k = 7 canonical, u32 / f32 rows)
     int fwd_fold = 1;     // long_kernel MODE_FWD (3 <= k <= 6 canonical, long sequences, u32 / f32 rows)
     int64_t fwd_min_len = 1024;   // mean sequence length from which MODE_FWD replaces seq_kernel mode 1
+    int bucket = 1;       // rows larger than shared memory: bucket_kernel + count_kernel instead of global atomics
+    int bucket_log2_seg = 14;   // columns per segment of that path (2^14 u32 bins = 64 KB of shared memory)
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
     int global_steps_per_warp = 1;
     int wave_persistent = 1;                 // global-atomic path as one cooperative launch (u32 / f32 output)
@@ -309,20 +314,28 @@ int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
         return fail(KTB_ERR_ARG, "long_kernel has no f64 instance");
     } else {
         const bool nrm = p.norm_mode != NORM_COUNTS;
+        const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
+        // 4 warps per CTA for reads of a few steps per warp (10 kbp = 20 steps: 5 per warp, balanced, half the per-warp
+        // set-up of 8 warps); 8 warps for long contigs
+        const int nw = h->long_warps > 0 ? h->long_warps : (mean_len <= 32768 ? 4 : 8);
         void (*kern)(const LongParams) = nullptr;
-        if (mode == MODE_K7) kern = nrm ? long_kernel<OUT, true, MODE_K7> : long_kernel<OUT, false, MODE_K7>;
-        else kern = nrm ? long_kernel<OUT, true, MODE_FWD> : long_kernel<OUT, false, MODE_FWD>;
+        if (mode == MODE_K7) {
+            if (nw == 4) kern = nrm ? long_kernel<OUT, true, MODE_K7, 4> : long_kernel<OUT, false, MODE_K7, 4>;
+            else kern = nrm ? long_kernel<OUT, true, MODE_K7, 8> : long_kernel<OUT, false, MODE_K7, 8>;
+        } else {
+            if (nw == 4) kern = nrm ? long_kernel<OUT, true, MODE_FWD, 4> : long_kernel<OUT, false, MODE_FWD, 4>;
+            else kern = nrm ? long_kernel<OUT, true, MODE_FWD, 8> : long_kernel<OUT, false, MODE_FWD, 8>;
+        }
         const size_t smem = ((((size_t)p.hist_words + 31) & ~(size_t)31) + p.dim) * 4;
         if (int rc = set_smem(kern, smem)) return rc;
         int per_sm = 1;
-        const int threads = LONG_WARPS * 32;
+        const int threads = nw * 32;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         if (per_sm < 1) per_sm = 1;
         uint64_t grid = (uint64_t)h->sm_count * per_sm;
-        const uint64_t nitems = ((p.n + p.group_size - 1) / p.group_size) * p.group_size;
+        const uint64_t nitems = ((p.n + SHORT_G - 1) / SHORT_G) * SHORT_G;
         if (grid > nitems) grid = nitems;
         if (grid < 1) grid = 1;
-        const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
         LongParams q = p;
         q.grab = h->seq_grab > 0 ? (uint32_t)h->seq_grab
                                  : (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(16, 4096 / std::max<uint64_t>(mean_len, 1)));
@@ -397,7 +410,8 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
             lp.counter = h->d_counters + 1;
             lp.list = sc.ok ? (const uint32_t *)h->ws_list.p : nullptr;
             lp.list_count = sc.ok ? h->d_counters + 2 : nullptr;
-            lp.group_size = SHORT_G;
+            lp.group_shift = 4;   // SHORT_G
+            static_assert(SHORT_G == 16, "group_shift");
             lp.k = h->k; lp.dim = (uint32_t)dim;
             lp.hist_words = long_mode == MODE_K7 ? K7_BINS : (uint32_t)h->ncodes + 4;
             lp.norm_mode = norm_mode; lp.canonical = canonical;
@@ -448,6 +462,58 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         h->stats.launches++;
         return KTB_OK;
     };
+    // ---- bucket-then-count (bucket_kernels.cuh): partition the column indices of every tile by their high bits,
+    // then count each (sequence, segment) in shared memory and write its part of the row once
+    const uint32_t log2_seg = (uint32_t)h->bucket_log2_seg;
+    const uint64_t nseg = (dim + (1ull << log2_seg) - 1) >> log2_seg;
+    const int bk_rank = !canonical ? 0 : (h->d_wave_tab && h->wave_smem_rank) ? 2 : 1;
+    const size_t bk_smem = (size_t)BK_STAGE_ENTRIES * 2 + (bk_rank == 2 ? (size_t)h->wave_tab_words * 6 : 0);
+    if (h->bucket && h->force_path == 0 && nseg <= (uint64_t)BK_MAX_SEG && (dim & 3) == 0 && h->k <= 15 &&
+        bk_smem + 1024 <= h->smem_optin && n < (1ull << 31) && total_bases < (1ull << 44)) {
+        const uint64_t tile_bases = (uint64_t)BK_TILE_CHUNKS * 16;
+        const uint64_t ntiles_bound = total_bases / tile_bases + 2 * n + 2;
+        if (ntiles_bound >= (1ull << 32)) return fail(KTB_ERR_ARG, "batch too large for the bucket path");
+        if (int rc = h->ws_tiles.ensure((n + 1) * 4)) return rc;
+        if (int rc = h->ws_pool.ensure((total_bases + 8 * nseg * ntiles_bound) * 2 + 64)) return rc;
+        if (int rc = h->ws_runs.ensure(ntiles_bound * nseg * sizeof(uint2))) return rc;
+        CU(cudaMemsetAsync(h->d_counters + 8, 0, 3 * sizeof(unsigned long long), st));
+        tile_prefix_kernel<<<1, 1024, 0, st>>>(d_offsets, n, (uint32_t)h->k, (uint32_t *)h->ws_tiles.p);
+        CU(cudaGetLastError());
+        h->stats.launches++;
+        BucketParams bp{};
+        bp.bases = d_bases; bp.offsets = d_offsets; bp.n = n; bp.total_bases = total_bases;
+        bp.tile_prefix = (const uint32_t *)h->ws_tiles.p;
+        bp.counter = h->d_counters + 8; bp.pool_top = h->d_counters + 9;
+        bp.pool = (uint16_t *)h->ws_pool.p; bp.runs = (uint2 *)h->ws_runs.p; bp.totals = tot;
+        bp.rank_full = h->d_rank_full; bp.rank_tab = h->d_wave_tab; bp.tab_words = bk_rank == 2 ? h->wave_tab_words : 0;
+        bp.k = (uint32_t)h->k; bp.nseg = (uint32_t)nseg; bp.log2_seg = log2_seg;
+        {
+            void (*kern)(const BucketParams) = bk_rank == 0 ? bucket_kernel<0> : bk_rank == 1 ? bucket_kernel<1> : bucket_kernel<2>;
+            if (int rc = set_smem(kern, bk_smem)) return rc;
+            const uint64_t grid = std::min<uint64_t>((uint64_t)h->sm_count, ntiles_bound);
+            kern<<<(unsigned)grid, BK_WARPS * 32, bk_smem, st>>>(bp);
+            CU(cudaGetLastError());
+            h->stats.launches++;
+        }
+        CountParams cp{};
+        cp.tile_prefix = bp.tile_prefix; cp.pool = bp.pool; cp.runs = bp.runs; cp.totals_in = tot;
+        cp.totals_out = d_totals; cp.out = d_out; cp.counter = h->d_counters + 10;
+        cp.n = n; cp.dim = dim; cp.nseg = (uint32_t)nseg; cp.log2_seg = log2_seg;
+        cp.norm_mode = norm_mode; cp.canonical = canonical;
+        {
+            const bool nrm = norm_mode != NORM_COUNTS;
+            void (*kern)(const CountParams) = nrm ? count_kernel<OUT, true> : count_kernel<OUT, false>;
+            const size_t smem = ((size_t)4 << log2_seg) * (OUT == OUT_F64 ? 1 : 2);
+            if (int rc = set_smem(kern, smem)) return rc;
+            int per_sm = 1;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CK_THREADS, smem));
+            const uint64_t grid = std::min<uint64_t>((uint64_t)h->sm_count * std::max(per_sm, 1), n * nseg);
+            kern<<<(unsigned)grid, CK_THREADS, smem, st>>>(cp);
+            CU(cudaGetLastError());
+            h->stats.launches++;
+        }
+        return KTB_OK;
+    }
     if (h->force_path == 1) {   // testing: the flat-decomposition fallback, whole batch at once
         uint32_t *counts = (uint32_t *)d_out;
         if (OUT == OUT_F64) {
@@ -794,7 +860,7 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
         CUB(cudaMemcpy(h->d_short_tab_canon, tc.data(), h->ncodes * 4, cudaMemcpyHostToDevice));
         CUB(cudaMemcpy(h->d_short_tab_raw, tr.data(), h->ncodes * 4, cudaMemcpyHostToDevice));
     }
-    CUB(cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)));
+    CUB(cudaMalloc(&h->d_counters, 16 * sizeof(unsigned long long)));
     for (auto &s : h->sets) {
         CUB(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         for (auto &e : s.ev) CUB(cudaEventCreate(&e));
@@ -830,6 +896,9 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     h->ws_counts.release();
     h->ws_list.release();
     h->ws_list2.release();
+    h->ws_tiles.release();
+    h->ws_pool.release();
+    h->ws_runs.release();
     if (h->d_rank_full) cudaFree(h->d_rank_full);
     if (h->d_canon_of_rank) cudaFree(h->d_canon_of_rank);
     if (h->d_canon_perm) cudaFree(h->d_canon_perm);
@@ -889,12 +958,20 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->short_variant = (int)value;
     } else if (!strcmp(key, "short_warps")) {
         h->short_warps = (int)value;
+    } else if (!strcmp(key, "long_warps")) {
+        if (value != 0 && value != 4 && value != 8) return fail(KTB_ERR_ARG, "long_warps must be 0, 4 or 8");
+        h->long_warps = (int)value;
     } else if (!strcmp(key, "k7_mid")) {
         h->k7_mid = (int)value;
     } else if (!strcmp(key, "fwd_fold")) {
         h->fwd_fold = (int)value;
     } else if (!strcmp(key, "fwd_min_len")) {
         h->fwd_min_len = value;
+    } else if (!strcmp(key, "bucket")) {
+        h->bucket = (int)value;
+    } else if (!strcmp(key, "bucket_log2_seg")) {
+        if (value < 10 || value > 15) return fail(KTB_ERR_ARG, "bucket_log2_seg must be in 10..15");
+        h->bucket_log2_seg = (int)value;
     } else if (!strcmp(key, "packed16")) {
         h->packed16 = (int)value;
     } else if (!strcmp(key, "even_rank")) {

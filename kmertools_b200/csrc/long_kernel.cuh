@@ -50,7 +50,7 @@ struct LongParams {
     unsigned long long *counter; // dynamic work counter (zeroed before launch)
     const uint32_t *list;        // groups to process (short_kernel's rejects); nullptr = every group
     const unsigned long long *list_count;
-    uint32_t group_size;
+    uint32_t group_shift;        // log2 of the sequences per group (SHORT_G = 16)
     uint32_t grab;               // consecutive work items per trip to the counter
     uint32_t k;
     uint32_t dim;
@@ -106,9 +106,77 @@ __device__ __forceinline__ void k7_keys_phase(uint32_t cf, uint32_t cf_prev, uin
     off[PHI] = k1 >> 16;
 }
 
-template <int OUT, bool NORM, int MODE>
-__global__ void __launch_bounds__(LONG_WARPS * 32, MODE == MODE_K7 ? 3 : 4) long_kernel(const LongParams p) {
+// ---- write-out of one row into the row image (normalisation fused), histogram re-initialised on the way.
+// SMALL: every count and the divisor are below 2^23 (exact in f32, magic-constant conversion valid).
+template <int OUT, bool NORM, int MODE, int NW, bool SMALL>
+__device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hbytes, uint32_t *stage, uint64_t dv) {
+    using T = typename OutT<OUT>::type;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float dF = (float)dv;
+    const float rinv = __frcp_rn(dF);
+    const double dD = (double)dv;
+    (void)dD;
+    if constexpr (MODE == MODE_K7) {
+        uint8_t *sbytes = reinterpret_cast<uint8_t *>(stage);
+        const uint4 *sched4 = reinterpret_cast<const uint4 *>(p.sched) + lane;
+        constexpr uint32_t niter = K7_BINS >> 7;   // 128 (bin, rank) pairs per warp iteration
+        const float nK = -8388608.0f * rinv;
+        (void)nK;
+        // the schedule comes from L2: two iterations in flight
+        uint4 e_a = __ldg(sched4 + warp * 32);
+        uint4 e_b = __ldg(sched4 + (warp + NW) * 32);
+#pragma unroll 2
+        for (uint32_t w = warp; w < niter; w += NW) {
+            const uint4 e4 = e_a;
+            e_a = e_b;
+            if (w + 2 * NW < niter) e_b = __ldg(sched4 + (w + 2 * NW) * 32);
+            const uint32_t ee[4] = {e4.x, e4.y, e4.z, e4.w};
+            uint32_t bits[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t *bin = reinterpret_cast<uint32_t *>(hbytes + (ee[q] & 0xFFFFu));
+                bits[q] = *bin;
+                *bin = FLOAT_2P23;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                T val;
+                if constexpr (OUT == OUT_U32) {
+                    val = bits[q] - FLOAT_2P23;
+                } else if constexpr (SMALL) {
+                    const float F = __uint_as_float(bits[q]);   // 2^23 + count
+                    const float cnt = F - 8388608.0f;
+                    if constexpr (NORM) {
+                        const float q0 = fmaf(F, rinv, nK);     // RN(count * rinv), as quot_f32
+                        const float rem = fmaf(-q0, dF, cnt);
+                        val = fmaf(rem, rinv, q0);
+                    } else {
+                        val = cnt;
+                    }
+                } else {
+                    const uint32_t cnt = bits[q] - FLOAT_2P23;
+                    val = NORM ? (float)((double)cnt / dD) : (float)cnt;
+                }
+                *reinterpret_cast<T *>(sbytes + (ee[q] >> 16)) = val;
+            }
+        }
+    } else {
+        for (uint32_t j = tid; j < p.dim; j += NW * 32) {
+            const uint32_t e = __ldg(p.sched + j);
+            uint32_t *a = reinterpret_cast<uint32_t *>(hbytes + (e & 0xFFFFu));
+            uint32_t *b = reinterpret_cast<uint32_t *>(hbytes + (e >> 16));
+            const uint32_t cnt = *a + *b;   // palindromes: b is the always-zero word
+            *a = 0;
+            *b = 0;
+            reinterpret_cast<T *>(stage)[j] = cvt_count<OUT, NORM, SMALL>(cnt, dF, rinv, dD);
+        }
+    }
+}
+
+template <int OUT, bool NORM, int MODE, int NW>
+__global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW == 8 ? 4 : 8)) long_kernel(const LongParams p) {
     static_assert(OUT == OUT_U32 || OUT == OUT_F32, "f64 rows keep seq_kernel");
+    static_assert(NW == 4 || NW == 8, "warps per CTA");
     extern __shared__ __align__(128) uint32_t lsm[];
     __shared__ unsigned long long s_item;
     __shared__ uint32_t s_total[2];
@@ -116,17 +184,16 @@ __global__ void __launch_bounds__(LONG_WARPS * 32, MODE == MODE_K7 ? 3 : 4) long
     uint32_t *hist = lsm;
     uint32_t *stage = lsm + ((p.hist_words + 31u) & ~31u);   // row image: dim x 4 bytes, 128-byte aligned
     uint8_t *hbytes = reinterpret_cast<uint8_t *>(hist);
-    uint8_t *sbytes = reinterpret_cast<uint8_t *>(stage);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t warp = tid >> 5;
-    constexpr uint32_t NW = LONG_WARPS;
     constexpr uint32_t FULL = 0xffffffffu;
     // MODE_K7 bins hold the float 2^23 + count (see header)
     constexpr uint32_t INIT = (MODE == MODE_K7) ? FLOAT_2P23 : 0u;
 
-    const uint64_t ngroups = p.list ? (uint64_t)*p.list_count : (p.n + p.group_size - 1) / p.group_size;
-    const uint64_t nitems = ngroups * p.group_size;
+    const uint32_t gshift = p.group_shift;
+    const uint64_t ngroups = p.list ? (uint64_t)*p.list_count : (p.n + (1ull << gshift) - 1) >> gshift;
+    const uint64_t nitems = ngroups << gshift;
     if ((uint64_t)blockIdx.x >= nitems) return;
     for (uint32_t i = tid; i < p.hist_words; i += NW * 32) hist[i] = INIT;
     if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
@@ -149,9 +216,9 @@ __global__ void __launch_bounds__(LONG_WARPS * 32, MODE == MODE_K7 ? 3 : 4) long
         if (item0 >= nitems) break;
         const unsigned long long item1 = min(item0 + grab, (unsigned long long)nitems);
         for (unsigned long long item = item0; item < item1; ++item) {
-            const uint64_t gi = item / p.group_size;
+            const uint64_t gi = item >> gshift;
             const uint64_t g = p.list ? (uint64_t)p.list[gi] : gi;
-            const uint64_t seq = g * (uint64_t)p.group_size + (item - gi * p.group_size);
+            const uint64_t seq = (g << gshift) + (item - (gi << gshift));
             if (seq >= p.n) continue;   // uniform for the CTA
             const uint64_t s0 = p.offsets[seq];
             const uint64_t s1 = p.offsets[seq + 1];
@@ -221,8 +288,7 @@ __global__ void __launch_bounds__(LONG_WARPS * 32, MODE == MODE_K7 ? 3 : 4) long
                 }
             }
             // ---- total = block sum of `mine`
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) mine += __shfl_xor_sync(FULL, mine, s);
+            mine = __reduce_add_sync(FULL, mine);
             if (lane == 0 && mine) atomicAdd(&s_total[it & 1], mine);
             // the row image is about to be overwritten: the bulk copy of the previous row must have read it
             if (tid == 0) bulk_wait_read();
@@ -231,63 +297,9 @@ __global__ void __launch_bounds__(LONG_WARPS * 32, MODE == MODE_K7 ? 3 : 4) long
             if (tid == 0) s_total[(it + 1) & 1] = 0;
             ++it;
             const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
-            const float dF = (float)dv;
-            const float rinv = __frcp_rn(dF);
-            const double dD = (double)dv;
             if (tid == 0 && p.totals) p.totals[seq] = total;
-            const bool small = dv < (1ULL << 23);   // counts and divisor exact in f32, magic-constant conversion valid
-
-            // ---- write-out into the row image (normalisation fused), histogram re-initialised on the way
-            if constexpr (MODE == MODE_K7) {
-                const uint4 *sched4 = reinterpret_cast<const uint4 *>(p.sched);
-                const uint32_t niter = p.dim >> 7;   // 128 (bin, rank) pairs per warp iteration
-                const float nK = -8388608.0f * rinv;
-                uint4 en = (warp < niter) ? __ldg(sched4 + warp * 32 + lane) : make_uint4(0, 0, 0, 0);
-                for (uint32_t w = warp; w < niter; w += NW) {
-                    const uint4 e4 = en;
-                    if (w + NW < niter) en = __ldg(sched4 + (w + NW) * 32 + lane);
-                    const uint32_t ee[4] = {e4.x, e4.y, e4.z, e4.w};
-                    uint32_t bits[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t *bin = reinterpret_cast<uint32_t *>(hbytes + (ee[q] & 0xFFFFu));
-                        bits[q] = *bin;
-                        *bin = INIT;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        T val;
-                        if constexpr (OUT == OUT_U32) {
-                            val = bits[q] - INIT;
-                        } else if (small) {
-                            const float F = __uint_as_float(bits[q]);   // 2^23 + count
-                            const float cnt = F - 8388608.0f;
-                            if constexpr (NORM) {
-                                const float q0 = fmaf(F, rinv, nK);        // RN(count * rinv), as quot_f32
-                                const float rem = fmaf(-q0, dF, cnt);
-                                val = fmaf(rem, rinv, q0);
-                            } else {
-                                val = cnt;
-                            }
-                        } else {
-                            const uint32_t cnt = bits[q] - INIT;
-                            val = NORM ? (float)((double)cnt / dD) : (float)cnt;
-                        }
-                        *reinterpret_cast<T *>(sbytes + (ee[q] >> 16)) = val;
-                    }
-                }
-            } else {
-                for (uint32_t j = tid; j < p.dim; j += NW * 32) {
-                    const uint32_t e = __ldg(p.sched + j);
-                    uint32_t *a = reinterpret_cast<uint32_t *>(hbytes + (e & 0xFFFFu));
-                    uint32_t *b = reinterpret_cast<uint32_t *>(hbytes + (e >> 16));
-                    const uint32_t cnt = *a + *b;   // palindromes: b is the always-zero word
-                    *a = 0;
-                    *b = 0;
-                    reinterpret_cast<T *>(stage)[j] = small ? cvt_count<OUT, NORM, true>(cnt, dF, rinv, dD)
-                                                            : cvt_count<OUT, NORM, false>(cnt, dF, rinv, dD);
-                }
-            }
+            if (dv < (1ULL << 23)) long_write_row<OUT, NORM, MODE, NW, true>(p, hbytes, stage, dv);
+            else long_write_row<OUT, NORM, MODE, NW, false>(p, hbytes, stage, dv);
             fence_async_smem();
             __syncthreads();
             if (tid == 0) bulk_store(out + seq * (uint64_t)p.dim, stage, p.dim * 4u);

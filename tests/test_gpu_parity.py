@@ -23,7 +23,8 @@ def comp(k):
 
 OPTION_DEFAULTS = (("force_path", 0), ("short_variant", 0), ("packed16", 1), ("even_rank", 1), ("dense_odd", 1),
                    ("wave_persistent", 1), ("wave_smem_rank", 1), ("wave_budget_bytes", 96 << 20),
-                   ("global_wave_bytes", 64 << 20), ("k7_mid", 1), ("fwd_fold", 1), ("fwd_min_len", 1024))
+                   ("global_wave_bytes", 64 << 20), ("k7_mid", 1), ("fwd_fold", 1), ("fwd_min_len", 1024),
+                   ("bucket", 1), ("bucket_log2_seg", 14), ("long_warps", 0))
 
 
 def check(k, bases, offsets, mins=True, norm_mode=NORM_CLI, dtype=np.float32, what="", **opts):
@@ -205,7 +206,7 @@ def test_global_path_many_waves(k, mins, persistent):
         budget = 3 * rows_per_wave * dim * 4 + 64
         # 1: cooperative launch, rank from shared-memory tables (k <= 10); 2: rank through the L2 table; 0: multi-launch
         opts = dict(wave_persistent=min(persistent, 1), wave_smem_rank=int(persistent == 1), global_wave_bytes=budget,
-                    wave_budget_bytes=budget)
+                    wave_budget_bytes=budget, bucket=0)
         check(k, bases, offsets, mins=mins, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"k{k} waves u32", **opts)
         check(k, bases, offsets, mins=mins, norm_mode=NORM_CLI, dtype=np.float32, what=f"k{k} waves f32", **opts)
     check(k, bases, offsets, mins=mins, norm_mode=NORM_PY, dtype=np.float32, what=f"k{k} py f32", **opts)
