@@ -104,6 +104,8 @@ struct ktb_oligo {
     uint32_t even_words = 0;
     uint32_t *d_wave_tab = nullptr;        // canonical-code bitmap + u32 pair prefixes for wave_kernel<2>
     uint32_t wave_tab_words = 0;
+    bool wave_tab_in_smem = false;         // the whole table fits shared memory (wave_kernel RANK 2)
+    bool wave_seg_aligned = false;         // every 2^13-code segment starts at a column that is a multiple of 4
     uint64_t mb_entries = 0;               // histogram words mode 4 needs (dense index + skew)
     uint32_t *d_k7_sched = nullptr;        // k = 7: conflict-free write-out schedule of long_kernel MODE_K7
     uint32_t *d_fwd_sched = nullptr;       // 3 <= k <= 6: (offset of c | offset of rc(c) << 16) per rank, long_kernel MODE_FWD
@@ -131,6 +133,7 @@ struct ktb_oligo {
     int fwd_fold = 1;     // long_kernel MODE_FWD (3 <= k <= 6 canonical, long sequences, u32 / f32 rows)
     int64_t fwd_min_len = 1024;   // mean sequence length from which MODE_FWD replaces seq_kernel mode 1
     int bucket = 1;       // rows larger than shared memory: bucket_kernel + count_kernel instead of global atomics
+    int bucket_blocks = 3;      // CTAs per SM bucket_kernel is compiled for (2 or 3)
     int bucket_log2_seg = 14;   // columns per segment of that path (2^14 u32 bins = 64 KB of shared memory)
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
     int global_steps_per_warp = 1;
@@ -462,48 +465,53 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         h->stats.launches++;
         return KTB_OK;
     };
-    // ---- bucket-then-count (bucket_kernels.cuh): partition the column indices of every tile by their high bits,
-    // then count each (sequence, segment) in shared memory and write its part of the row once
+    // ---- bucket-then-count (bucket_kernels.cuh): partition the k-mer codes of every tile by their high bits, then
+    // count each (sequence, code segment) in shared memory and write its part of the row once
     const uint32_t log2_seg = (uint32_t)h->bucket_log2_seg;
-    const uint64_t nseg = (dim + (1ull << log2_seg) - 1) >> log2_seg;
-    const int bk_rank = !canonical ? 0 : (h->d_wave_tab && h->wave_smem_rank) ? 2 : 1;
-    const size_t bk_smem = (size_t)BK_STAGE_ENTRIES * 2 + (bk_rank == 2 ? (size_t)h->wave_tab_words * 6 : 0);
-    if (h->bucket && h->force_path == 0 && nseg <= (uint64_t)BK_MAX_SEG && (dim & 3) == 0 && h->k <= 15 &&
-        bk_smem + 1024 <= h->smem_optin && n < (1ull << 31) && total_bases < (1ull << 44)) {
+    const uint64_t nseg = (h->ncodes + (1ull << log2_seg) - 1) >> log2_seg;
+    if (h->bucket && h->force_path == 0 && nseg <= (uint64_t)BK_MAX_SEG && (dim & 3) == 0 && h->k <= 10 &&
+        (!canonical || (h->d_wave_tab && h->wave_seg_aligned)) && n < (1ull << 31) && total_bases < (1ull << 44)) {
         const uint64_t tile_bases = (uint64_t)BK_TILE_CHUNKS * 16;
         const uint64_t ntiles_bound = total_bases / tile_bases + 2 * n + 2;
-        if (ntiles_bound >= (1ull << 32)) return fail(KTB_ERR_ARG, "batch too large for the bucket path");
-        if (int rc = h->ws_tiles.ensure((n + 1) * 4)) return rc;
-        if (int rc = h->ws_pool.ensure((total_bases + 8 * nseg * ntiles_bound) * 2 + 64)) return rc;
-        if (int rc = h->ws_runs.ensure(ntiles_bound * nseg * sizeof(uint2))) return rc;
+        if (ntiles_bound >= (1ull << 31)) return fail(KTB_ERR_ARG, "batch too large for the bucket path");
+        if (int rc = h->ws_tiles.ensure((n + 1) * 4 + 64 + ntiles_bound * sizeof(TileInfo))) return rc;
+        if (int rc = h->ws_pool.ensure(ntiles_bound * (uint64_t)BK_TILE_CAP * 2 + 64)) return rc;
+        if (int rc = h->ws_runs.ensure(ntiles_bound * nseg * 4)) return rc;
+        uint32_t *tile_prefix = (uint32_t *)h->ws_tiles.p;
+        TileInfo *tiles = (TileInfo *)((uint8_t *)h->ws_tiles.p + (((n + 1) * 4 + 63) & ~(uint64_t)63));
         CU(cudaMemsetAsync(h->d_counters + 8, 0, 3 * sizeof(unsigned long long), st));
-        tile_prefix_kernel<<<1, 1024, 0, st>>>(d_offsets, n, (uint32_t)h->k, (uint32_t *)h->ws_tiles.p);
+        tile_prefix_kernel<<<1, 1024, 0, st>>>(d_offsets, n, (uint32_t)h->k, tile_prefix, tiles);
         CU(cudaGetLastError());
         h->stats.launches++;
         BucketParams bp{};
-        bp.bases = d_bases; bp.offsets = d_offsets; bp.n = n; bp.total_bases = total_bases;
-        bp.tile_prefix = (const uint32_t *)h->ws_tiles.p;
-        bp.counter = h->d_counters + 8; bp.pool_top = h->d_counters + 9;
-        bp.pool = (uint16_t *)h->ws_pool.p; bp.runs = (uint2 *)h->ws_runs.p; bp.totals = tot;
-        bp.rank_full = h->d_rank_full; bp.rank_tab = h->d_wave_tab; bp.tab_words = bk_rank == 2 ? h->wave_tab_words : 0;
+        bp.bases = d_bases; bp.n = n; bp.total_bases = total_bases;
+        bp.tile_prefix = tile_prefix; bp.tiles = tiles;
+        bp.pool = (uint16_t *)h->ws_pool.p; bp.runs = (uint32_t *)h->ws_runs.p; bp.totals = tot;
         bp.k = (uint32_t)h->k; bp.nseg = (uint32_t)nseg; bp.log2_seg = log2_seg;
         {
-            void (*kern)(const BucketParams) = bk_rank == 0 ? bucket_kernel<0> : bk_rank == 1 ? bucket_kernel<1> : bucket_kernel<2>;
-            if (int rc = set_smem(kern, bk_smem)) return rc;
-            const uint64_t grid = std::min<uint64_t>((uint64_t)h->sm_count, ntiles_bound);
-            kern<<<(unsigned)grid, BK_WARPS * 32, bk_smem, st>>>(bp);
+            void (*kern)(const BucketParams) =
+                h->bucket_blocks == 2 ? (canonical ? bucket_kernel<true, 2> : bucket_kernel<false, 2>)
+                                      : (canonical ? bucket_kernel<true, 3> : bucket_kernel<false, 3>);
+            int per_sm = 1;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BK_WARPS * 32, 0));
+            const uint64_t grid = std::min<uint64_t>((uint64_t)h->sm_count * std::max(per_sm, 1), ntiles_bound);
+            kern<<<(unsigned)grid, BK_WARPS * 32, 0, st>>>(bp);
             CU(cudaGetLastError());
             h->stats.launches++;
         }
         CountParams cp{};
-        cp.tile_prefix = bp.tile_prefix; cp.pool = bp.pool; cp.runs = bp.runs; cp.totals_in = tot;
+        cp.tile_prefix = tile_prefix; cp.pool = bp.pool; cp.runs = bp.runs; cp.totals_in = tot;
         cp.totals_out = d_totals; cp.out = d_out; cp.counter = h->d_counters + 10;
+        cp.rank_tab = h->d_wave_tab; cp.tab_words = h->wave_tab_words;
         cp.n = n; cp.dim = dim; cp.nseg = (uint32_t)nseg; cp.log2_seg = log2_seg;
         cp.norm_mode = norm_mode; cp.canonical = canonical;
         {
             const bool nrm = norm_mode != NORM_COUNTS;
-            void (*kern)(const CountParams) = nrm ? count_kernel<OUT, true> : count_kernel<OUT, false>;
-            const size_t smem = ((size_t)4 << log2_seg) * (OUT == OUT_F64 ? 1 : 2);
+            void (*kern)(const CountParams) =
+                canonical ? (nrm ? count_kernel<OUT, true, true> : count_kernel<OUT, false, true>)
+                          : (nrm ? count_kernel<OUT, true, false> : count_kernel<OUT, false, false>);
+            const size_t S = (size_t)1 << log2_seg;
+            const size_t smem = (S + S / 32 + S / 64) * 4;
             if (int rc = set_smem(kern, smem)) return rc;
             int per_sm = 1;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CK_THREADS, smem));
@@ -547,7 +555,7 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         // a wave is a third of the budget: the wave being counted and the next one (zeroed at the end of the
         // iteration) are live together, the rest is slack for lines on their way out (32 MB waves measured best)
         wp.wave_rows = std::max<uint64_t>(1, std::min<uint64_t>(256, (uint64_t)h->wave_budget_bytes / 3 / row_bytes));
-        const int rank_mode = !canonical ? 0 : (h->d_wave_tab && h->wave_smem_rank) ? 2 : 1;
+        const int rank_mode = !canonical ? 0 : (h->d_wave_tab && h->wave_tab_in_smem && h->wave_smem_rank) ? 2 : 1;
         wp.rank_tab = h->d_wave_tab; wp.tab_words = h->wave_tab_words;
         constexpr bool F32 = (OUT == OUT_F32);
         const void *kern = rank_mode == 0 ? (const void *)wave_kernel<0, F32>
@@ -818,7 +826,9 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
             CUB(cudaMemcpy(h->d_k7_sched, sched.data(), sched.size() * 4, cudaMemcpyHostToDevice));
         }
     }
-    if (k >= 3 && k <= 6 && (h->dim_canon % 4) == 0) {   // long_kernel MODE_FWD: fold table, rank -> (c, rc(c))
+    // long_kernel MODE_FWD: fold table, rank -> (c, rc(c)).  k = 6 stays with seq_kernel: its fold gathers hist[rc(c)] for
+    // consecutive c, which differ in their TOP digits, i.e. 32 lanes in one bank (measured 2x slower, profiles/r2_sweeps.txt)
+    if (k >= 3 && k <= 5 && (h->dim_canon % 4) == 0) {
         std::vector<uint32_t> sched(h->dim_canon);
         for (uint64_t j = 0; j < h->dim_canon; ++j) {
             const uint32_t c = h->canon_of_rank[j], r = (uint32_t)rev_comp(c, k);
@@ -827,14 +837,17 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
         CUB(cudaMalloc(&h->d_fwd_sched, sched.size() * 4));
         CUB(cudaMemcpy(h->d_fwd_sched, sched.data(), sched.size() * 4, cudaMemcpyHostToDevice));
     }
-    {   // wave_kernel<2>: rank(c) = prefix[w / 2] + popc(bits below c) for canonical c, tables in shared memory
+    {   // bitmap of the canonical codes + running rank per pair of words: rank(c) = prefix[w / 2] + popc(bits below c).
+        // wave_kernel<2> keeps the whole table in shared memory (k <= 10); count_kernel loads one segment's slice.
         const uint64_t words = h->ncodes / 32;
         const uint64_t bytes = words * 4 + (words / 2) * 4;
-        if (h->ncodes >= 64 && h->dim_canon * 4 > 64 * 1024 && bytes + 4096 <= h->smem_optin) {
+        if (h->ncodes >= 64 && h->dim_canon * 4 > 64 * 1024) {
             std::vector<uint32_t> tab(words + words / 2, 0);
             uint32_t running = 0;
+            bool aligned = true;
             for (uint64_t w = 0; w < words; ++w) {
                 if (!(w & 1)) tab[words + w / 2] = running;
+                if ((w & 255) == 0 && (running & 3)) aligned = false;   // segment boundaries (2^13 codes and coarser)
                 uint32_t bits = 0;
                 for (uint32_t i = 0; i < 32; ++i) {
                     const uint64_t x = 32 * w + i;
@@ -844,6 +857,8 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
                 running += (uint32_t)__builtin_popcount(bits);
             }
             h->wave_tab_words = (uint32_t)words;
+            h->wave_tab_in_smem = bytes + 4096 <= h->smem_optin;
+            h->wave_seg_aligned = aligned;
             CUB(cudaMalloc(&h->d_wave_tab, tab.size() * 4));
             CUB(cudaMemcpy(h->d_wave_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
         }
@@ -969,8 +984,11 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->fwd_min_len = value;
     } else if (!strcmp(key, "bucket")) {
         h->bucket = (int)value;
+    } else if (!strcmp(key, "bucket_blocks")) {
+        if (value != 2 && value != 3) return fail(KTB_ERR_ARG, "bucket_blocks must be 2 or 3");
+        h->bucket_blocks = (int)value;
     } else if (!strcmp(key, "bucket_log2_seg")) {
-        if (value < 10 || value > 15) return fail(KTB_ERR_ARG, "bucket_log2_seg must be in 10..15");
+        if (value < 13 || value > 14) return fail(KTB_ERR_ARG, "bucket_log2_seg must be 13 or 14");
         h->bucket_log2_seg = (int)value;
     } else if (!strcmp(key, "packed16")) {
         h->packed16 = (int)value;

@@ -24,9 +24,22 @@ bool format_from_path(const std::string &path_in, SeqFormat *out) {
     return false;
 }
 
+// gzip input: flate2::read::GzDecoder (ktio/src/seq.rs:149) decodes the FIRST member of the file and reports end of
+// stream there; zlib's gzread() would run on into further members, so the stream is inflated by hand.
+struct GzState {
+    z_stream zs;
+    std::vector<uint8_t> in;
+    bool done = false;      // first member finished
+    GzState() : in(1u << 20) { memset(&zs, 0, sizeof zs); }
+};
+
 ByteSource::~ByteSource() {
-    if (gz_) gzclose((gzFile)gz_);
-    else if (own_fd_ && fd_ >= 0) ::close(fd_);
+    if (gz_) {
+        GzState *g = (GzState *)gz_;
+        inflateEnd(&g->zs);
+        delete g;
+    }
+    if (own_fd_ && fd_ >= 0) ::close(fd_);
 }
 
 bool ByteSource::open(const std::string &path, std::string *err) {
@@ -42,12 +55,13 @@ bool ByteSource::open(const std::string &path, std::string *err) {
     }
     own_fd_ = true;
     if (ends_with(path, ".gz")) {
-        gz_ = gzdopen(fd_, "rb");
-        if (!gz_) {
+        GzState *g = new GzState();
+        if (inflateInit2(&g->zs, 16 + MAX_WBITS) != Z_OK) {   // 16: expect a gzip header, as GzDecoder does
+            delete g;
             if (err) *err = "Unable to open: " + path;
             return false;
         }
-        gzbuffer((gzFile)gz_, 1 << 20);
+        gz_ = g;
     }
     return true;
 }
@@ -63,9 +77,25 @@ long ByteSource::read(void *buf, size_t n) {
         if (n == 1) return 1;
     }
     if (gz_) {
-        const int r = gzread((gzFile)gz_, p + got, (unsigned)std::min<size_t>(n - got, 1u << 30));
-        if (r < 0) return -1;
-        return (long)(got + r);
+        GzState *g = (GzState *)gz_;
+        if (g->done) return (long)got;
+        g->zs.next_out = p + got;
+        g->zs.avail_out = (unsigned)std::min<size_t>(n - got, 1u << 30);
+        const unsigned want = g->zs.avail_out;
+        while (g->zs.avail_out == want) {   // until something was produced, the member ended, or the file did
+            if (g->zs.avail_in == 0) {
+                ssize_t r;
+                do { r = ::read(fd_, g->in.data(), g->in.size()); } while (r < 0 && errno == EINTR);
+                if (r < 0) return -1;
+                if (r == 0) return (want == g->zs.avail_out && !g->done) ? -1 : (long)(got + want - g->zs.avail_out);  // truncated member
+                g->zs.next_in = g->in.data();
+                g->zs.avail_in = (unsigned)r;
+            }
+            const int rc = inflate(&g->zs, Z_NO_FLUSH);
+            if (rc == Z_STREAM_END) { g->done = true; break; }
+            if (rc != Z_OK && rc != Z_BUF_ERROR) return -1;
+        }
+        return (long)(got + want - g->zs.avail_out);
     }
     for (;;) {
         const ssize_t r = ::read(fd_, p + got, n - got);
@@ -202,45 +232,59 @@ long FastxParser::fill(uint8_t *bases, size_t cap, size_t *used, std::vector<uin
         ++nrec_;
         return true;
     };
-    while ((size_t)added < max_records) {
+    while ((size_t)added < max_records && !stopped_) {
         rec_start = w = *used;
         overflow = false;
         if (fmt_ == SeqFormat::Fasta) {
+            // bio::io::fasta::Reader::read (rust-bio 2.3.0): the first line of the input must start with '>' (a blank
+            // line there is an error too); the sequence is every following line, trailing whitespace trimmed, up to
+            // the next line that starts with '>' or the end of input.
             if (!have_header_) {
                 if (!next_line(&lp, &ln)) break;  // end of input
                 if (ln == 0 || lp[0] != '>') {
-                    if (trim_end(lp, ln) == 0) continue;  // tolerate blank lines between records
                     err_ = "Expected > at record start.";
                     return -1;
                 }
                 have_header_ = true;
+                header_blank_ = trim_end(lp + 1, ln - 1) == 0;
             }
-            bool more = false;
+            bool more = false, next_blank = false;
             while (next_line(&lp, &ln)) {
-                if (ln > 0 && lp[0] == '>') { more = true; break; }
+                if (ln > 0 && lp[0] == '>') { more = true; next_blank = trim_end(lp + 1, ln - 1) == 0; break; }
                 put(lp, trim_end(lp, ln));
             }
+            // Records::next stops at the first EMPTY record (no id, no description, no sequence): a bare ">" line
+            // directly followed by another header or the end of input ends the iteration, whatever follows.
+            if (header_blank_ && !overflow && w == rec_start) {
+                have_header_ = false;
+                stopped_ = true;
+                break;
+            }
             have_header_ = more;  // the '>' line just consumed opens the next record
+            header_blank_ = next_blank;
         } else {
+            // bio::io::fastq::Reader::read (rust-bio 2.3.0): '@' line (anything else, a blank line included, is
+            // Error::MissingAt), sequence lines up to the first line starting with '+', then exactly as many quality
+            // lines as there were sequence lines; an empty quality string is Error::IncompleteRecord.
             if (!next_line(&lp, &ln)) break;
             if (ln == 0 || lp[0] != '@') {
-                if (trim_end(lp, ln) == 0) continue;
                 err_ = "Expected @ at record start.";
                 return -1;
             }
-            size_t lines = 0;
-            bool plus = false;
+            size_t lines = 0, qual = 0;
             while (next_line(&lp, &ln)) {
-                if (ln > 0 && lp[0] == '+') { plus = true; break; }
+                if (ln > 0 && lp[0] == '+') break;
                 put(lp, trim_end(lp, ln));
                 ++lines;
             }
-            if (!plus) {
+            for (size_t i = 0; i < lines; ++i) {
+                if (!next_line(&lp, &ln)) break;  // quality lines are only measured
+                qual += trim_end(lp, ln);
+            }
+            if (qual == 0) {
                 err_ = "Incomplete record. Each FastQ record has to consist of 4 lines: header, sequence, separator and qualities.";
                 return -1;
             }
-            for (size_t i = 0; i < lines; ++i)
-                if (!next_line(&lp, &ln)) break;  // quality lines are skipped
         }
         if (!commit()) return added;
     }

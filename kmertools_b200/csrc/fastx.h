@@ -9,8 +9,14 @@
 //     sequence with trailing whitespace trimmed (multi-line records are concatenated)
 //   * FASTQ: '@' header, sequence lines up to the '+' line, then as many quality lines as sequence lines
 //   * ".gz" paths are inflated (zlib), "-" is stdin (seq.rs:141-155)
-// Only what the reference's own tests pin (seq.rs:164-233) is parity-checked; CRLF, blank lines and
-// multi-member gzip follow the published rust-bio behaviour but are unpinned.
+// The reference's own tests pin multi-line FASTA, ids, single-member gzip and a missing final newline
+// (seq.rs:164-233).  Everything else follows the published source of the two readers and of flate2, restated in
+// fastx.cpp next to each rule and pinned by tests/test_io_host.py: CRLF (trailing whitespace of every line is
+// trimmed), blank lines (part of a FASTA sequence; Error::MissingAt where a FASTQ header is expected, also at the
+// end of the file; "Expected > at record start." as the first line of a FASTA file), multi-line FASTQ (quality lines
+// are counted, so '@' / '>' may start one), an empty quality string (Error::IncompleteRecord), a bare '>' record
+// (ends the iteration) and multi-member gzip (flate2::read::GzDecoder stops after the first member).  The crates
+// themselves cannot be executed here (no Rust toolchain), so these are restatements, not differential tests.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -51,7 +57,7 @@ public:
     // records appended, 0 at end of input, -1 on a parse error (message in error()).  A record larger
     // than the free space of an EMPTY buffer sets need_bytes() so the caller can grow it.
     long fill(uint8_t *bases, size_t cap, size_t *used, std::vector<uint64_t> *offsets, size_t max_records);
-    bool eof() const { return eof_ && pending_.empty() && !in_record_; }
+    bool eof() const { return stopped_ || (eof_ && pos_ == end_ && pending_.empty() && !in_record_ && !have_header_); }
     size_t need_bytes() const { return need_; }
     const std::string &error() const { return err_; }
     uint64_t records() const { return nrec_; }
@@ -71,6 +77,8 @@ private:
     size_t need_ = 0;
     uint64_t nrec_ = 0;
     bool have_header_ = false;       // FASTA: a '>' line has been consumed and its record is open
+    bool header_blank_ = false;      // FASTA: that line carried neither an id nor a description
+    bool stopped_ = false;           // FASTA: an empty record ended the iteration (bio::io::fasta::Records::next)
 };
 
 }  // namespace ktb

@@ -1,9 +1,11 @@
 // file_api.cu — file-level driver behind `kmertools comp oligo` (see include/kmertools_b200.h).
 // Host side: streaming FASTA/FASTQ parse into pinned, offset-indexed buffers; two buffer sets so that
-// parsing batch b+1 overlaps the GPU work and the D2H copy of batch b; sequential writes keep the
-// reference's row order.  Device side: counts (short/seq/flat kernels) + format_norm_kernel.
+// parsing batch b+1 overlaps the GPU work and the D2H copy of batch b; finished batches go to an ordered
+// asynchronous writer (span_writer.h: `-t` threads copy disjoint spans into a shared mapping of the output, as the
+// reference's mmap writer does), so writing batch b also overlaps batch b+1.  Device side: counts + format_norm_kernel.
 #include "../../include/kmertools_b200.h"
 #include "fastx.h"
+#include "span_writer.h"
 #include "textfmt.cuh"
 
 #include <charconv>
@@ -14,6 +16,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 int ktb_internal_dispatch(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n,
@@ -78,6 +81,9 @@ struct Set {
     cudaEvent_t kernels_done = nullptr;
     uint64_t n = 0, nbases = 0, out_bytes = 0;
     bool pending = false;
+    bool writing = false;                      // rows handed to the writer, buffers not reusable yet
+    ktb::SpanWriter::Ticket ticket;
+    std::vector<std::vector<char>> parts;      // host-formatted text (counts / CGR), one part per formatting thread
     ~Set() {
         if (kernels_done) cudaEventDestroy(kernels_done);
         if (stream) cudaStreamDestroy(stream);
@@ -111,6 +117,8 @@ SetPair *acquire_sets(int device) {
     for (auto &s : sp->sets) {
         s.n = s.nbases = s.out_bytes = 0;
         s.pending = false;
+        s.writing = false;
+        s.ticket = ktb::SpanWriter::Ticket();
         if ((!s.stream && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) ||
             (!s.kernels_done && cudaEventCreateWithFlags(&s.kernels_done, cudaEventDisableTiming) != cudaSuccess)) {
             delete sp;
@@ -133,12 +141,12 @@ void release_sets(SetPair *sp) {
     delete old;
 }
 
-// u32 counts -> "c0<d>c1<d>...\n" (format!("{}", f64) prints integral values without ".0", oligo.rs:138)
-size_t format_counts_rows(const uint32_t *counts, uint64_t n, uint32_t dim, char delim, std::vector<char> *out) {
-    out->resize((size_t)n * dim * 11 + 16);
+// u32 counts of rows [r0, r1) -> "c0<d>c1<d>...\n" (format!("{}", f64) prints integral values without ".0", oligo.rs:138)
+void format_counts_rows(const uint32_t *counts, uint64_t r0, uint64_t r1, uint32_t dim, char delim, std::vector<char> *out) {
+    out->resize((size_t)(r1 - r0) * dim * 11 + 16);
     char *o = out->data();
     size_t w = 0;
-    for (uint64_t i = 0; i < n * (uint64_t)dim; ++i) {
+    for (uint64_t i = r0 * (uint64_t)dim; i < r1 * (uint64_t)dim; ++i) {
         uint32_t v = counts[i];
         char tmp[10];
         int len = 0;
@@ -146,9 +154,20 @@ size_t format_counts_rows(const uint32_t *counts, uint64_t n, uint32_t dim, char
         while (len) o[w++] = tmp[--len];
         o[w++] = ((i + 1) % dim == 0) ? '\n' : delim;
     }
-    return w;
+    out->resize(w);
 }
 
+// rows [0, n) cut into `threads` contiguous ranges, fn(r0, r1, part) run on one thread each (the `-t` of the CLI)
+template <typename F>
+void format_parallel(uint64_t n, int threads, std::vector<std::vector<char>> *parts, F fn) {
+    const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, n));
+    parts->resize(nt);
+    if (nt == 1) { fn(0, n, &(*parts)[0]); return; }
+    std::vector<std::thread> th;
+    for (uint64_t t = 0; t < nt; ++t)
+        th.emplace_back([&, t] { fn(n * t / nt, n * (t + 1) / nt, &(*parts)[t]); });
+    for (auto &x : th) x.join();
+}
 
 // Rust's `{}` for f64: shortest digits that round-trip, never an exponent (std::to_chars fixed does the same)
 inline char *put_f64(char *o, double v) {
@@ -186,14 +205,14 @@ void cgr_prefixes(const ktb_oligo *h, int k, uint64_t dim, double vecsize, std::
     }
 }
 
-// rows -> "(x,y,freq) (x,y,freq) ...\n" (oligocgr.rs:88-101)
-size_t format_cgr_rows(const void *rows, bool norm, uint64_t n, uint32_t dim, const std::vector<std::string> &pref,
-                       std::vector<char> *out) {
+// rows [r0, r1) -> "(x,y,freq) (x,y,freq) ...\n" (oligocgr.rs:88-101)
+void format_cgr_rows(const void *rows, bool norm, uint64_t r0, uint64_t r1, uint32_t dim, const std::vector<std::string> &pref,
+                     std::vector<char> *out) {
     size_t plen = 0;
     for (auto &p : pref) plen += p.size();
-    out->resize((size_t)n * (plen + (size_t)dim * 420) + 16);
+    out->resize((size_t)(r1 - r0) * (plen + (size_t)dim * 420) + 16);
     char *o = out->data();
-    for (uint64_t i = 0; i < n; ++i) {
+    for (uint64_t i = r0; i < r1; ++i) {
         for (uint32_t j = 0; j < dim; ++j) {
             memcpy(o, pref[j].data(), pref[j].size());
             o += pref[j].size();
@@ -203,7 +222,7 @@ size_t format_cgr_rows(const void *rows, bool norm, uint64_t n, uint32_t dim, co
             *o++ = (j + 1 == dim) ? '\n' : ' ';
         }
     }
-    return (size_t)(o - out->data());
+    out->resize((size_t)(o - out->data()));
 }
 
 }  // namespace
@@ -276,26 +295,27 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
     struct Guard { ktb_oligo *h; ~Guard() { ktb_oligo_destroy(h); } } guard{h};
     const uint64_t dim = ktb_oligo_dim(h, cgr ? 1 : o->canonical);
 
-    FILE *fo = fopen(o->out_path, "wb");
-    if (!fo) return ktb_internal_fail(KTB_ERR_IO, (std::string("Unable to write to file: ") + o->out_path).c_str());
-    struct FGuard { FILE *f; ~FGuard() { if (f) fclose(f); } } fguard{fo};
-    std::vector<char> iobuf(8u << 20);
-    setvbuf(fo, iobuf.data(), _IOFBF, iobuf.size());
+    // `-t` (kmertools/src/args.rs:249-251; 0 = all cores): threads of the output writer and of the host formatter
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int nthreads = o->threads > 0 ? std::min(o->threads, 64) : std::min(hw, 8);
+    ktb::SpanWriter wr;
+    if (!wr.open(o->out_path, nthreads, &err)) return ktb_internal_fail(KTB_ERR_IO, err.c_str());
+    ktb::SpanWriter::Ticket header_ticket;
+    std::string header_line;
 
     std::vector<std::string> cgr_pref;
     if (cgr) cgr_prefixes(h, o->k, dim, (double)cgr_vecsize, &cgr_pref);
     if (o->header && !cgr) {  // get_header().join(delim) + "\n", oligo.rs:114-117
         std::vector<char> hb(dim * o->k);
         if (int rc = ktb_oligo_header(h, o->canonical, hb.data(), hb.size())) return rc;
-        std::string line;
+        std::string &line = header_line;
         line.reserve(dim * (o->k + 1));
         for (uint64_t j = 0; j < dim; ++j) {
             if (j) line.push_back(o->delim);
             line.append(hb.data() + j * o->k, o->k);
         }
         line.push_back('\n');
-        fwrite(line.data(), 1, line.size(), fo);
-        st.bytes_written += line.size();
+        wr.submit(line.data(), line.size(), &header_ticket);
     }
 
     // ---- batch geometry
@@ -304,7 +324,8 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
     // batches of 64 MB of output / 32 MB of bases: page-locking the two buffer sets is the fixed cost of a run
     // (~0.5 ms per MB; 1 GB of text: 752 ms -> 370 ms, 293 ms with the cached sets), and a batch this size already
     // hides every launch latency.
-    // Measured and not kept: 8 threads of pwrite per batch (buffered writes to one file serialise in the kernel).
+    // Round 1 measured 8 threads of pwrite per batch and dropped them (write()/pwrite() on one file serialise on the
+    // inode lock); the writer now copies spans through a shared mapping instead, which does not.
     const size_t OUT_CAP = 64u << 20;
     const size_t max_records = std::max<size_t>(1, std::min<size_t>(OUT_CAP / out_per_row, 4u << 20));
     size_t bases_cap = 32u << 20;
@@ -320,11 +341,22 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
     SetPair *pair = acquire_sets(o->device);
     if (!pair) return ktb_internal_fail(KTB_ERR_CUDA, "cudaStreamCreate failed");
     struct PairGuard { SetPair *p; ~PairGuard() { release_sets(p); } } pair_guard{pair};
+    // on every exit the writer threads stop BEFORE the buffer sets they read from go back to the pool
+    struct WriterGuard { ktb::SpanWriter *w; ~WriterGuard() { w->close(); } } writer_guard{&wr};
     Set *sets = pair->sets;
     cudaEvent_t prev_kernels_done = nullptr;   // the handle's work counters / scratch are shared: kernels of
                                                // consecutive batches are chained, copies still overlap
-    std::vector<char> text;
     uint64_t launches = 0;
+    double writer_wait_ms = 0;
+    // the rows of a set are with the writer until its ticket completes; only then may its buffers be reused
+    auto reclaim = [&](Set &s) -> int {
+        if (!s.writing) return KTB_OK;
+        const double t0 = now_ms();
+        const bool ok = wr.wait(&s.ticket);
+        writer_wait_ms += now_ms() - t0;
+        s.writing = false;
+        return ok ? KTB_OK : ktb_internal_fail(KTB_ERR_IO, "write to the output file failed");
+    };
 
     auto finish = [&](Set &s) -> int {  // wait for the batch, write its rows
         if (!s.pending) return KTB_OK;
@@ -333,20 +365,22 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
             return ktb_internal_fail(KTB_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
         const double t1 = now_ms();
         st.gpu_wait_ms += t1 - t0;
-        size_t w;
         if (gpu_text) {
-            w = fwrite(s.h_out.p, 1, s.out_bytes, fo);
-            if (w != s.out_bytes) return ktb_internal_fail(KTB_ERR_IO, "short write");
-        } else if (cgr) {
-            const size_t len = format_cgr_rows(s.h_out.p, norm, s.n, (uint32_t)dim, cgr_pref, &text);
-            w = fwrite(text.data(), 1, len, fo);
-            if (w != len) return ktb_internal_fail(KTB_ERR_IO, "short write");
+            wr.submit(s.h_out.p, s.out_bytes, &s.ticket);
         } else {
-            const size_t len = format_counts_rows((const uint32_t *)s.h_out.p, s.n, (uint32_t)dim, o->delim, &text);
-            w = fwrite(text.data(), 1, len, fo);
-            if (w != len) return ktb_internal_fail(KTB_ERR_IO, "short write");
+            const uint32_t *counts = (const uint32_t *)s.h_out.p;
+            const void *rows = s.h_out.p;
+            if (cgr)
+                format_parallel(s.n, nthreads, &s.parts, [&](uint64_t r0, uint64_t r1, std::vector<char> *part) {
+                    format_cgr_rows(rows, norm, r0, r1, (uint32_t)dim, cgr_pref, part);
+                });
+            else
+                format_parallel(s.n, nthreads, &s.parts, [&](uint64_t r0, uint64_t r1, std::vector<char> *part) {
+                    format_counts_rows(counts, r0, r1, (uint32_t)dim, o->delim, part);
+                });
+            for (auto &part : s.parts) wr.submit(part.data(), part.size(), &s.ticket);
         }
-        st.bytes_written += w;
+        s.writing = true;
         st.write_ms += now_ms() - t1;
         s.pending = false;
         return KTB_OK;
@@ -358,7 +392,8 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
     int b = 0;
     for (;;) {
         Set &s = sets[b & 1];
-        if (int rc = finish(s)) return rc;   // this set's previous batch (b-2) must be written first
+        if (int rc = finish(s)) return rc;   // this set's previous batch (b-2) goes to the writer first ...
+        if (int rc = reclaim(s)) return rc;  // ... and must have left the buffers
         const double ta0 = now_ms();
         if (!s.h_bases.ensure(bases_cap)) return ktb_internal_fail(KTB_ERR_NOMEM, "pinned allocation failed");
         const double tp0 = now_ms();
@@ -427,13 +462,21 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
     // drain in order: the older batch first
     if (int rc = finish(sets[b & 1])) return rc;
     if (int rc = finish(sets[(b + 1) & 1])) return rc;
-    if (fflush(fo) != 0) return ktb_internal_fail(KTB_ERR_IO, "flush failed");
+    if (int rc = reclaim(sets[b & 1])) return rc;
+    if (int rc = reclaim(sets[(b + 1) & 1])) return rc;
+    if (!wr.wait(&header_ticket)) return ktb_internal_fail(KTB_ERR_IO, "write to the output file failed");
+    st.write_ms += writer_wait_ms;
+    st.bytes_written = wr.bytes();
+    const int wthreads = wr.threads();
+    const bool wmapped = wr.mapped();
+    if (!wr.close()) return ktb_internal_fail(KTB_ERR_IO, "closing the output file failed");
     st.launches = launches;
     st.total_ms = now_ms() - t_start;
     if (getenv("KTB_FILE_TRACE"))
         fprintf(stderr, "[ktb file] setup %.1f ms (handle, output file, streams), buffers %.1f ms, parse %.1f ms, gpu wait %.1f ms, "
-                        "write %.1f ms, total %.1f ms\n", t_loop - t_start, alloc_ms, st.parse_ms, st.gpu_wait_ms, st.write_ms,
-                st.total_ms);
+                        "output %.1f ms on the caller (%.1f ms waiting for the %d %s writer thread(s)), total %.1f ms\n",
+                t_loop - t_start, alloc_ms, st.parse_ms, st.gpu_wait_ms, st.write_ms, writer_wait_ms, wthreads,
+                wmapped ? "mapping" : "sequential", st.total_ms);
     if (stats) *stats = st;
     return KTB_OK;
 }

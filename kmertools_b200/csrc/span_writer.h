@@ -1,0 +1,166 @@
+// span_writer.h — ordered, asynchronous output of the file-level drivers.
+//
+// The reference pre-sizes its output and lets N workers write disjoint rows through a shared mapping
+// (composition/src/oligo.rs:167-229, ktio/src/mmap.rs:6-47: memmap2 + write_at).  Same idea here, batch-wise: the
+// caller hands over a finished block of text; its file offset is fixed at that moment (submission order = file
+// order), the file is extended, and a small pool of threads copies 8 MB spans of the block into a shared mapping
+// of their part of the file.  Mapped copies do not take the inode write lock that serialises write()/pwrite() on
+// one file, so the spans really proceed in parallel (page allocation included), and the caller goes on parsing the
+// next batch while they do.  Outputs that cannot be mapped (pipes, character devices, /dev/stdout) are written with
+// write() by ONE pool thread in submission order.
+#pragma once
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace ktb {
+
+class SpanWriter {
+public:
+    // one submitted block; wait() on it before the memory it points at is reused
+    struct Ticket {
+        int pending = 0;
+        bool failed = false;
+    };
+
+    SpanWriter() = default;
+    ~SpanWriter() { close(); }
+    SpanWriter(const SpanWriter &) = delete;
+    SpanWriter &operator=(const SpanWriter &) = delete;
+
+    bool open(const char *path, int threads, std::string *err) {
+        fd_ = ::open(path, O_RDWR | O_CREAT | O_TRUNC, 0644);
+        if (fd_ < 0) fd_ = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);   // e.g. a write-only device
+        if (fd_ < 0) {
+            if (err) *err = std::string("Unable to write to file: ") + path;
+            return false;
+        }
+        struct stat sb;
+        mapped_ = fstat(fd_, &sb) == 0 && S_ISREG(sb.st_mode) && (fcntl(fd_, F_GETFL) & O_ACCMODE) == O_RDWR;
+        if (mapped_) {   // some file systems refuse shared mappings: probe once
+            if (ftruncate(fd_, 4096) != 0) mapped_ = false;
+            else {
+                void *m = mmap(nullptr, 4096, PROT_READ | PROT_WRITE, MAP_SHARED, fd_, 0);
+                if (m == MAP_FAILED) mapped_ = false; else munmap(m, 4096);
+                if (ftruncate(fd_, 0) != 0) mapped_ = false;
+            }
+        }
+        const int nt = mapped_ ? (threads < 1 ? 1 : (threads > 64 ? 64 : threads)) : 1;
+        for (int i = 0; i < nt; ++i) pool_.emplace_back([this] { work(); });
+        return true;
+    }
+
+    int threads() const { return (int)pool_.size(); }
+    bool mapped() const { return mapped_; }
+    uint64_t bytes() const { return cursor_; }
+
+    // Appends [data, data+len) to the file (asynchronously).  `t` must stay alive until wait(t).
+    void submit(const void *data, size_t len, Ticket *t) {
+        if (!len) return;
+        const uint64_t off = cursor_;
+        cursor_ += len;
+        if (mapped_ && ftruncate(fd_, (off_t)cursor_) != 0) {
+            std::lock_guard<std::mutex> lk(mu_);
+            t->failed = true;
+            return;
+        }
+        const size_t span = mapped_ ? kSpan : len;
+        std::lock_guard<std::mutex> lk(mu_);
+        for (size_t a = 0; a < len; a += span) {
+            jobs_.push_back(Job{(const char *)data + a, off + a, std::min(span, len - a), t});
+            ++t->pending;
+        }
+        cv_.notify_all();
+    }
+
+    // true when every span of the ticket's blocks reached the file
+    bool wait(Ticket *t) {
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return t->pending == 0; });
+        const bool ok = !t->failed;
+        t->failed = false;
+        return ok;
+    }
+
+    bool close() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            cv_.notify_all();
+        }
+        for (auto &th : pool_) th.join();
+        pool_.clear();
+        bool ok = true;
+        if (fd_ >= 0) {
+            ok = ::close(fd_) == 0;
+            fd_ = -1;
+        }
+        return ok;
+    }
+
+private:
+    static constexpr size_t kSpan = 8u << 20;
+    struct Job {
+        const char *src;
+        uint64_t off;
+        size_t len;
+        Ticket *t;
+    };
+
+    bool put(const Job &j) {
+        if (mapped_) {
+            const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
+            const uint64_t a = j.off & ~(page - 1);
+            const size_t maplen = (size_t)(j.off - a) + j.len;
+            void *m = mmap(nullptr, maplen, PROT_READ | PROT_WRITE, MAP_SHARED, fd_, (off_t)a);
+            if (m == MAP_FAILED) return false;
+            memcpy((char *)m + (j.off - a), j.src, j.len);
+            return munmap(m, maplen) == 0;
+        }
+        size_t w = 0;
+        while (w < j.len) {   // sequential sink: one thread, submission order
+            const ssize_t r = ::write(fd_, j.src + w, j.len - w);
+            if (r <= 0) return false;
+            w += (size_t)r;
+        }
+        return true;
+    }
+
+    void work() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !jobs_.empty(); });
+                if (jobs_.empty()) return;
+                j = jobs_.front();
+                jobs_.pop_front();
+            }
+            const bool ok = put(j);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (!ok) j.t->failed = true;
+            if (--j.t->pending == 0) done_.notify_all();
+        }
+    }
+
+    int fd_ = -1;
+    bool mapped_ = false;
+    uint64_t cursor_ = 0;
+    std::vector<std::thread> pool_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::deque<Job> jobs_;
+    bool stop_ = false;
+};
+
+}  // namespace ktb

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 from kmertools_b200._lib import NORM_CLI, NORM_COUNTS, NORM_PY  # noqa: E402
 
-TILE = 992 * 16   # bases per tile of bucket_kernel
+TILE = 496 * 16   # bases per tile of bucket_kernel
 
 
 @pytest.mark.parametrize("k,mins", [(9, True), (10, True), (8, False), (9, False)])
@@ -32,16 +32,17 @@ def test_bucket_path_ragged(k, mins):
         check(k, bases, offsets, mins=mins, norm_mode=NORM_COUNTS, dtype=np.float64, what=f"bucket k{k} f64 counts")
 
 
-@pytest.mark.parametrize("log2_seg", [12, 13, 15])
+@pytest.mark.parametrize("log2_seg", [13, 14])
 def test_bucket_segment_sizes(log2_seg):
     rng = np.random.default_rng(77 + log2_seg)
     lengths = np.r_[rng.integers(0, 50_000, size=12), [TILE * 2 + 7]]
     bases, offsets = random_batch(rng, lengths, noise=0.002, n_runs=0.2)
     check(9, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"k9 seg 2^{log2_seg}", bucket_log2_seg=log2_seg)
     check(9, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, what=f"k9 seg 2^{log2_seg} f32", bucket_log2_seg=log2_seg)
-    if log2_seg >= 13:
-        check(10, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"k10 seg 2^{log2_seg}",
-              bucket_log2_seg=log2_seg)
+    check(8, bases, offsets, mins=False, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"raw k8 seg 2^{log2_seg}",
+          bucket_log2_seg=log2_seg)
+    check(10, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"k10 seg 2^{log2_seg} (2^13: falls back)",
+          bucket_log2_seg=log2_seg, bucket_blocks=2)
 
 
 def test_bucket_low_complexity_and_unaligned_starts():
@@ -59,7 +60,7 @@ def test_bucket_low_complexity_and_unaligned_starts():
 
 
 def test_bucket_one_long_contig():
-    """A 3 Mbp contig = 190 tiles of one sequence: count_kernel walks 190 runs per segment."""
+    """A 3 Mbp contig = 379 tiles of one sequence: count_kernel walks 379 runs per segment."""
     rng = np.random.default_rng(5)
     bases, offsets = random_batch(rng, [700, 3_000_000, 0, 2500], noise=0.0005, n_runs=0.5)
     check(9, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what="k9 long contig")
