@@ -279,7 +279,6 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="skip the file-level (FASTQ -> text) driver sample")
-    ap.add_argument("--short-variant", type=int, default=None)
     ap.add_argument("--force-path", type=int, default=None)
     ap.add_argument("--seq-threads", type=int, default=None)
     ap.add_argument("--global-wave-mb", type=int, default=None)
@@ -314,8 +313,6 @@ def main():
     code, npdt, esize = DT[spec["dtype"]]
     dim = dim_of(k)
     oc = OligoComputer(k, device=local)
-    if args.short_variant is not None:
-        oc.set_option("short_variant", args.short_variant)
     if args.force_path is not None:
         oc.set_option("force_path", args.force_path)
     if args.seq_threads is not None:

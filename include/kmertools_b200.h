@@ -141,7 +141,13 @@ int ktb_oligo_last_stats(const ktb_oligo *h, ktb_stats *out);
  *   "wave_smem_rank"     1 (default): that kernel computes canonical ranks from shared-memory tables (k <= 10)
  *   "wave_budget_bytes"  L2 budget of that kernel; a wave (rows zeroed, counted and normalised together) is a third of it
  *   "global_wave_bytes"  bytes of output rows zeroed + counted together by the multi-launch variant (fits L2)
- *   "short_warps", "short_variant"  accepted for compatibility with earlier revisions, no effect on results */
+ *   "bucket"             1 (default): rows larger than shared memory (canonical k = 9, 10; raw k = 8..10) are built by
+ *                        bucket_kernel + count_kernel (partition by code segment, count in shared memory); 0: wave_kernel
+ *   "bucket_log2_seg"    log2 of the codes per segment of that path (13 or 14)
+ *   "k7_mid"             1: k = 7 rows by long_kernel (middle-base-first keys, scheduled write-out); 0: seq_kernel mode 4
+ *   "fwd_fold"           1 (default): 3 <= k <= 5 rows of long sequences by long_kernel (forward codes folded at write-out)
+ *   "fwd_min_len"        mean sequence length from which "fwd_fold" applies
+ *   "long_warps"         warps per CTA of long_kernel (0 = heuristic, 4 or 8) */
 int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value);
 
 /* Pinned host memory for callers that want asynchronous copies. */
@@ -190,6 +196,11 @@ void ktb_release_cached_buffers(void);
  * sniff != 0: format from the first byte, else from the extension. */
 int ktb_fastx_load(const char *path, int sniff, uint8_t **bases, uint64_t **offsets, uint64_t *n);
 void ktb_free(void *p);
+
+/* ktb_fastx_load through the BATCH loop of the file-level drivers (at most max_records records and batch_bytes bytes of
+ * sequence per batch), so tests can put batch boundaries anywhere in a file.  Same outputs as ktb_fastx_load. */
+int ktb_debug_fastx_batches(const char *path, int sniff, uint64_t max_records, uint64_t batch_bytes, uint8_t **bases,
+                            uint64_t **offsets, uint64_t *n);
 
 /* Host build of the GPU text formatter: 8 characters "d.dddddd" = Rust's format!("{:.6}", q), q in [0,1]. */
 int ktb_debug_format6(double q, char *out8);

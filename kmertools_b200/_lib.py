@@ -63,6 +63,7 @@ SYMBOLS = {
     "ktb_comp_cgr_file": (_I, [C.POINTER(FileOpts), _I, C.POINTER(FileStats)]),
     "ktb_release_cached_buffers": (None, []),
     "ktb_fastx_load": (_I, [C.c_char_p, _I, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_U64)]),
+    "ktb_debug_fastx_batches": (_I, [C.c_char_p, _I, _U64, _U64, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_U64)]),
     "ktb_free": (None, [_VP]),
     "ktb_debug_format6": (_I, [C.c_double, C.c_char_p]),
     "ktb_debug_nt4_table": (_I, [_VP, _VP]),

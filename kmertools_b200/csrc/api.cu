@@ -122,8 +122,6 @@ struct ktb_oligo {
     // options
     int64_t chunk_bytes = 512ll << 20;
     int force_path = 0;
-    int short_variant = 0;
-    int short_warps = 0;  // 0 = auto
     int seq_threads = 0;  // 0 = auto (256)
     int seq_grab = 0;     // work items per atomic in seq_kernel (0 = from the mean sequence length)
     int dense_odd = 1;    // use seq_kernel mode 4 where it applies
@@ -133,7 +131,6 @@ struct ktb_oligo {
     int fwd_fold = 1;     // long_kernel MODE_FWD (3 <= k <= 6 canonical, long sequences, u32 / f32 rows)
     int64_t fwd_min_len = 1024;   // mean sequence length from which MODE_FWD replaces seq_kernel mode 1
     int bucket = 1;       // rows larger than shared memory: bucket_kernel + count_kernel instead of global atomics
-    int bucket_blocks = 3;      // CTAs per SM bucket_kernel is compiled for (2 or 3)
     int bucket_log2_seg = 14;   // columns per segment of that path (2^14 u32 bins = 64 KB of shared memory)
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
     int global_steps_per_warp = 1;
@@ -185,7 +182,6 @@ int launch_short(ktb_oligo *h, const ShortParams &p, const ShortCfg &c, cudaStre
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SHORT_WARPS * 32, c.smem));
     if (per_sm < 1) per_sm = 1;
-    if (h->short_warps > 0) per_sm = std::min(per_sm, std::max(1, h->short_warps / SHORT_WARPS));
     uint64_t grid = (uint64_t)h->sm_count * per_sm;
     const uint64_t need = (p.ngroups + SHORT_WARPS - 1) / SHORT_WARPS;
     if (grid > need) grid = need;
@@ -320,10 +316,12 @@ int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
         const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
         // 4 warps per CTA for reads of a few steps per warp (10 kbp = 20 steps: 5 per warp, balanced, half the per-warp
         // set-up of 8 warps); 8 warps for long contigs
-        const int nw = h->long_warps > 0 ? h->long_warps : (mean_len <= 32768 ? 4 : 8);
+        int nw = h->long_warps > 0 ? h->long_warps : (mean_len <= 32768 ? 4 : 8);
+        if (nw == 10 && mode != MODE_K7) nw = 8;
         void (*kern)(const LongParams) = nullptr;
         if (mode == MODE_K7) {
             if (nw == 4) kern = nrm ? long_kernel<OUT, true, MODE_K7, 4> : long_kernel<OUT, false, MODE_K7, 4>;
+            else if (nw == 10) kern = nrm ? long_kernel<OUT, true, MODE_K7, 10> : long_kernel<OUT, false, MODE_K7, 10>;
             else kern = nrm ? long_kernel<OUT, true, MODE_K7, 8> : long_kernel<OUT, false, MODE_K7, 8>;
         } else {
             if (nw == 4) kern = nrm ? long_kernel<OUT, true, MODE_FWD, 4> : long_kernel<OUT, false, MODE_FWD, 4>;
@@ -489,9 +487,7 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         bp.pool = (uint16_t *)h->ws_pool.p; bp.runs = (uint32_t *)h->ws_runs.p; bp.totals = tot;
         bp.k = (uint32_t)h->k; bp.nseg = (uint32_t)nseg; bp.log2_seg = log2_seg;
         {
-            void (*kern)(const BucketParams) =
-                h->bucket_blocks == 2 ? (canonical ? bucket_kernel<true, 2> : bucket_kernel<false, 2>)
-                                      : (canonical ? bucket_kernel<true, 3> : bucket_kernel<false, 3>);
+            void (*kern)(const BucketParams) = canonical ? bucket_kernel<true> : bucket_kernel<false>;
             int per_sm = 1;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BK_WARPS * 32, 0));
             const uint64_t grid = std::min<uint64_t>((uint64_t)h->sm_count * std::max(per_sm, 1), ntiles_bound);
@@ -511,7 +507,7 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
                 canonical ? (nrm ? count_kernel<OUT, true, true> : count_kernel<OUT, false, true>)
                           : (nrm ? count_kernel<OUT, true, false> : count_kernel<OUT, false, false>);
             const size_t S = (size_t)1 << log2_seg;
-            const size_t smem = (S + S / 32 + S / 64) * 4;
+            const size_t smem = (S + 2 * (S / 32 + S / 64)) * 4;
             if (int rc = set_smem(kern, smem)) return rc;
             int per_sm = 1;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CK_THREADS, smem));
@@ -969,12 +965,8 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->chunk_bytes = value;
     } else if (!strcmp(key, "force_path")) {
         h->force_path = (int)value;
-    } else if (!strcmp(key, "short_variant")) {
-        h->short_variant = (int)value;
-    } else if (!strcmp(key, "short_warps")) {
-        h->short_warps = (int)value;
     } else if (!strcmp(key, "long_warps")) {
-        if (value != 0 && value != 4 && value != 8) return fail(KTB_ERR_ARG, "long_warps must be 0, 4 or 8");
+        if (value != 0 && value != 4 && value != 8 && value != 10) return fail(KTB_ERR_ARG, "long_warps must be 0, 4, 8 or 10");
         h->long_warps = (int)value;
     } else if (!strcmp(key, "k7_mid")) {
         h->k7_mid = (int)value;
@@ -984,9 +976,6 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->fwd_min_len = value;
     } else if (!strcmp(key, "bucket")) {
         h->bucket = (int)value;
-    } else if (!strcmp(key, "bucket_blocks")) {
-        if (value != 2 && value != 3) return fail(KTB_ERR_ARG, "bucket_blocks must be 2 or 3");
-        h->bucket_blocks = (int)value;
     } else if (!strcmp(key, "bucket_log2_seg")) {
         if (value < 13 || value > 14) return fail(KTB_ERR_ARG, "bucket_log2_seg must be 13 or 14");
         h->bucket_log2_seg = (int)value;

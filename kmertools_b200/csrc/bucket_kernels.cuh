@@ -28,14 +28,14 @@
 
 namespace ktb {
 
-constexpr int BK_WARPS = 8;                  // bucket_kernel: 256 threads
-constexpr int BK_STEPS_PER_WARP = 2;
+constexpr int BK_WARPS = 8;                  // bucket_kernel: 256 threads, one 31-chunk step per warp
 constexpr int BK_CHUNKS_PER_STEP = 31;       // lane 0 of a step only provides the look-back chunk
-constexpr int BK_TILE_CHUNKS = BK_WARPS * BK_STEPS_PER_WARP * BK_CHUNKS_PER_STEP;   // 496 chunks = 7,936 bases
+constexpr int BK_TILE_CHUNKS = BK_WARPS * BK_CHUNKS_PER_STEP;       // 248 chunks = 3,968 bases (positions fit 12 bits)
 constexpr int BK_MAX_SEG = 64;
 constexpr int BK_TILE_CAP = BK_TILE_CHUNKS * 16 + BK_MAX_SEG * 8;   // pool entries per tile (runs padded to 8 entries)
 constexpr int CK_THREADS = 256;              // count_kernel
 constexpr int CK_WARPS = CK_THREADS / 32;
+constexpr int CK_MAXD = 256;                 // run descriptors of one (sequence, segment) handled per pass
 
 // everything bucket_kernel needs to know about a tile, written once by tile_prefix_kernel (32 bytes = two 128-bit
 // loads that do not depend on each other, prefetched one tile ahead)
@@ -99,12 +99,11 @@ __global__ void __launch_bounds__(1024) tile_prefix_kernel(const uint64_t *offse
     if (tid == 1023) tile_prefix[n] = s_part[1023];
 }
 
-// MB: CTAs per SM the register allocation aims at (3: 80 registers and ~50 spilled words per tile; 2: 128 registers)
-template <bool CANON, int MB>
-__global__ void __launch_bounds__(BK_WARPS * 32, MB) bucket_kernel(const BucketParams p) {
-    __shared__ __align__(128) uint16_t stage[BK_TILE_CAP];
+template <bool CANON>
+__global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketParams p) {
+    __shared__ __align__(128) uint16_t stage[BK_TILE_CAP + 32];   // sorted tile; the last 32 entries swallow invalid windows
     __shared__ uint32_t s_cnt[BK_MAX_SEG + 1];  // codes of this tile per segment; [nseg] collects the invalid windows
-    __shared__ uint32_t s_base[BK_MAX_SEG];     // first staging entry of the segment's run (multiple of 8)
+    __shared__ uint32_t s_base[BK_MAX_SEG + 1]; // first staging entry of the segment's run (multiple of 8); [nseg] = trash
     __shared__ uint32_t s_tot;
     __shared__ uint32_t s_copy;                 // entries of the sorted tile (runs padded to multiples of 8)
 
@@ -118,68 +117,62 @@ __global__ void __launch_bounds__(BK_WARPS * 32, MB) bucket_kernel(const BucketP
     const uint64_t ntiles = p.tile_prefix[p.n];
     const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
 
-    // tiles cost the same, so they are dealt out statically (tile b, b + grid, ...): the next tile's record is loaded
-    // while the current one is processed and no work counter sits on the critical path
+    // chunk of this lane in a tile: lane l > 0 owns chunk c, lane 0 holds the chunk before lane 1's (look-back only)
+    auto chunk_of = [&](const TileInfo &ti) -> int64_t {
+        return (int64_t)ti.tile * BK_TILE_CHUNKS + (int64_t)warp * BK_CHUNKS_PER_STEP + lane - 1;
+    };
+    auto load_chunk = [&](const TileInfo &ti) -> uint4 {
+        const int64_t c = chunk_of(ti);
+        const uint64_t cbase = ti.q0 >> 4;
+        const int64_t nch = (int64_t)(((ti.q1 - 1) >> 4) - cbase) + 1;
+        return (c >= 0 && c < nch) ? load16_guarded(p.bases, (cbase + (uint64_t)c) << 4, p.total_bases) : filler;
+    };
+
+    // tiles cost the same, so they are dealt out statically (tile b, b + grid, ...): the next tile's record and bases
+    // are loaded while the current tile is processed; no work counter, no load on the critical path
     uint64_t tile_id = blockIdx.x;
-    TileInfo cur{};
-    if (tile_id < ntiles) cur = p.tiles[tile_id];
+    if (tile_id >= ntiles) return;
+    TileInfo ti = p.tiles[tile_id];
+    uint4 v = load_chunk(ti);
     for (; tile_id < ntiles; tile_id += gridDim.x) {
-        const TileInfo ti = cur;
-        if (tile_id + gridDim.x < ntiles) cur = p.tiles[tile_id + gridDim.x];
-        if (tid == 0) s_tot = 0;
+        const bool more = tile_id + gridDim.x < ntiles;
+        TileInfo nti = ti;
+        if (more) nti = p.tiles[tile_id + gridDim.x];
+        if (tid == 0) { s_tot = 0; s_base[trash] = BK_TILE_CAP; }
         if (tid <= BK_MAX_SEG) s_cnt[tid] = 0;
         __syncthreads();
-        const uint64_t seq = ti.seq;
-        const uint32_t tile = ti.tile;
         const uint64_t q0 = ti.q0, q1 = ti.q1;
-        const uint64_t cbase = q0 >> 4;
-        const uint32_t nch = (uint32_t)(((q1 - 1) >> 4) - cbase) + 1u;
-        const uint32_t head_mask = 0xFFFFu >> (uint32_t)(q0 & 15);
-        const uint32_t tail_mask = ~(0xFFFFu >> ((uint32_t)((q1 - 1) & 15) + 1u)) & 0xFFFFu;
+        const int64_t nch = (int64_t)(((q1 - 1) >> 4) - (q0 >> 4)) + 1;
+        const int64_t c = chunk_of(ti);
 
         // ---- phase 1: code of every window of the tile, position inside its segment's run (atomics WITH return)
-        // per window: code (20 bits, k <= 10) | low 12 bits of the position << 20; bit 12 of the position in `hib`
-        uint32_t cp[BK_STEPS_PER_WARP][16];
-        uint32_t hib[BK_STEPS_PER_WARP];
-        uint32_t vws[BK_STEPS_PER_WARP];
-        uint32_t mine = 0;
-#pragma unroll
-        for (int s = 0; s < BK_STEPS_PER_WARP; ++s) {
-            // lane l > 0 owns chunk c; lane 0 holds the chunk before lane 1's (look-back only, emits nothing)
-            const int64_t c = (int64_t)tile * BK_TILE_CHUNKS + (int64_t)(warp * BK_STEPS_PER_WARP + s) * BK_CHUNKS_PER_STEP + lane - 1;
-            const bool inside = c >= 0 && c < (int64_t)nch;
-            const uint4 v = inside ? load16_guarded(p.bases, (cbase + (uint64_t)c) << 4, p.total_bases) : filler;
-            uint32_t cf, vm;
-            decode16(v, cf, vm);
-            if (!inside) vm = 0;
-            if (c == 0) vm &= head_mask;
-            if (c == (int64_t)nch - 1) vm &= tail_mask;
-            const uint32_t cf_prev = __shfl_up_sync(FULL, cf, 1);
-            const uint32_t vm_prev = __shfl_up_sync(FULL, vm, 1);
-            uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
-            if (lane == 0) vw = 0;
-            vws[s] = vw;
-            mine += __popc(vw);
-            const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
-            uint64_t R64 = 0;
-            if constexpr (CANON) R64 = ((uint64_t)revcomp_pack(cf) << 32) | revcomp_pack(cf_prev);
-            uint32_t hb = 0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t f = (uint32_t)(F64 >> (2 * (15 - j))) & kmask;
-                uint32_t code = f;
-                if constexpr (CANON) {
-                    const uint32_t r = (uint32_t)(R64 >> (2 * (17 + j - (int)k))) & kmask;
-                    code = min(f, r);
-                }
-                // invalid windows queue up in the trash segment: no branch around the atomic
-                const uint32_t sg = (vw & (1u << (15 - j))) ? (code >> p.log2_seg) : trash;
-                const uint32_t ps = atomicAdd(&s_cnt[sg], 1u);
-                cp[s][j] = code | (ps << 20);
-                hb |= ((ps >> 12) & 1u) << j;
-            }
-            hib[s] = hb;
+        uint32_t cf, vm;
+        decode16(v, cf, vm);
+        if (c < 0 || c >= nch) vm = 0;
+        if (c == 0) vm &= 0xFFFFu >> (uint32_t)(q0 & 15);
+        if (c == nch - 1) vm &= ~(0xFFFFu >> ((uint32_t)((q1 - 1) & 15) + 1u)) & 0xFFFFu;
+        const uint32_t cf_prev = __shfl_up_sync(FULL, cf, 1);
+        const uint32_t vm_prev = __shfl_up_sync(FULL, vm, 1);
+        uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
+        if (lane == 0) vw = 0;
+        uint32_t mine = __popc(vw);
+        // reverse strand, shifted once so that window j sits at bit 2j: base i of R64 is at bit 2(i + 16)
+        uint32_t rlo = 0, rhi = 0;
+        if constexpr (CANON) {
+            const uint64_t R64 = (((uint64_t)revcomp_pack(cf) << 32) | revcomp_pack(cf_prev)) >> (2 * (17 - (int)k));
+            rlo = (uint32_t)R64; rhi = (uint32_t)(R64 >> 32);
         }
+        uint32_t cp[16];   // per window: code (20 bits, k <= 10) | position in the run << 20 (12 bits)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            uint32_t code = ((j < 15) ? __funnelshift_r(cf, cf_prev, 2 * (15 - j)) : cf) & kmask;
+            if constexpr (CANON) code = min(code, ((j > 0) ? __funnelshift_r(rlo, rhi, 2 * j) : rlo) & kmask);
+            // invalid windows queue up in the trash segment: no branch around the atomic
+            const uint32_t sg = (vw & (1u << (15 - j))) ? (code >> p.log2_seg) : trash;
+            const uint32_t ps = atomicAdd(&s_cnt[sg], 1u);
+            cp[j] = code | (ps << 20);
+        }
+        if (more) v = load_chunk(nti);   // the next tile's bases are on their way while this tile is sorted
         mine = __reduce_add_sync(FULL, mine);
         if (lane == 0 && mine) atomicAdd(&s_tot, mine);
         // the staging buffer is about to be overwritten: the previous tile's bulk copy must have read it
@@ -202,25 +195,24 @@ __global__ void __launch_bounds__(BK_WARPS * 32, MB) bucket_kernel(const BucketP
             if (2 * lane < (int)p.nseg) { s_base[2 * lane] = b0; rd[2 * lane] = ((b0 >> 3) << 16) | c0; }
             if (2 * lane + 1 < (int)p.nseg) { s_base[2 * lane + 1] = b1; rd[2 * lane + 1] = ((b1 >> 3) << 16) | c1; }
             if (lane == 31) s_copy = incl;
-            if (lane == 0 && s_tot) atomicAdd(p.totals + seq, (unsigned long long)s_tot);
+            if (lane == 0 && s_tot) atomicAdd(p.totals + ti.seq, (unsigned long long)s_tot);
         }
         __syncthreads();
 
-        // ---- phase 3: scatter the in-segment codes to their runs, one bulk copy of the sorted tile into its pool slot
+        // ---- phase 3: scatter the in-segment codes to their runs (branch-free: invalid windows land in the trash
+        // entries), then one bulk copy of the sorted tile into its pool slot
 #pragma unroll
-        for (int s = 0; s < BK_STEPS_PER_WARP; ++s) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (vws[s] & (1u << (15 - j))) {
-                    const uint32_t code = cp[s][j] & 0xFFFFFu;
-                    const uint32_t ps = (cp[s][j] >> 20) | (((hib[s] >> j) & 1u) << 12);
-                    stage[s_base[code >> p.log2_seg] + ps] = (uint16_t)(code & seg_mask);
-                }
-            }
+        for (int j = 0; j < 16; ++j) {
+            const bool ok = (vw & (1u << (15 - j))) != 0u;
+            const uint32_t code = cp[j] & 0xFFFFFu;
+            const uint32_t sg = ok ? (code >> p.log2_seg) : trash;
+            const uint32_t ps = ok ? (cp[j] >> 20) : (uint32_t)lane;
+            stage[s_base[sg] + ps] = (uint16_t)(code & seg_mask);
         }
         fence_async_smem();
         __syncthreads();
         if (tid == 0 && s_copy) bulk_store(p.pool + tile_id * BK_TILE_CAP, stage, s_copy * 2u);
+        ti = nti;
     }
     if (tid == 0) bulk_wait_all();
 }
@@ -244,38 +236,49 @@ struct CountParams {
 };
 
 // One CTA per (sequence, segment of the code space).  The columns of the segment are [R, R + bins): R = rank of the
-// segment's first code.  u32 / f32 parts of a row leave as one bulk copy, f64 parts are stored directly.
+// segment's first code.  The runs of the segment (one per tile of the sequence) are flattened into units of four codes
+// and dealt to the threads, so all of them are in flight together; the first unit of every thread, the descriptors and
+// the segment's rank tables are loaded BEFORE the CTA waits for the bulk copy of its previous part to leave the
+// histogram, so the two latencies overlap.  u32 / f32 parts leave as one bulk copy, f64 parts are stored directly.
 template <int OUT, bool NORM, bool CANON>
 __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams p) {
     extern __shared__ __align__(128) uint32_t csm[];
     __shared__ unsigned long long s_item;
+    __shared__ uint32_t s_unit[CK_MAXD + 1];   // exclusive prefix of the runs' unit counts
+    __shared__ uint32_t s_src[CK_MAXD];        // first pool entry of the run / 8
+    __shared__ uint32_t s_len[CK_MAXD];        // codes in the run
+    __shared__ uint32_t s_wsum[CK_WARPS];
     using T = typename OutT<OUT>::type;
     const uint32_t S = 1u << p.log2_seg;                 // codes per segment
+    const uint32_t tabw = S / 32 + S / 64;               // words of one copy of the segment's rank tables
     uint32_t *hist = csm;                                // up to S bins
-    uint32_t *s_bits = csm + S;                          // CANON: S / 32 bitmap words of the segment
-    uint32_t *s_pref = s_bits + S / 32;                  // CANON: S / 64 running ranks, relative to the segment's first column
+    uint32_t *tabs = csm + S;                            // CANON: two copies (items alternate)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t FULL = 0xffffffffu;
     const uint64_t nitems = p.n * p.nseg;
     // items differ in cost (segments hold between none and twice the average number of k-mers), so they are dealt out
     // dynamically; the counter is read one item ahead to keep its round trip off the critical path
     unsigned long long next_item = 0;
     if (tid == 0) next_item = atomicAdd(p.counter, 1ULL);
+    uint32_t it = 0;
+    bool in_flight = false;   // (tid 0) a bulk copy out of `hist` may still be reading it
     for (;;) {
         if (tid == 0) {
-            if constexpr (OUT != OUT_F64) bulk_wait_read();   // the previous part has left the histogram
             s_item = next_item;
             next_item = atomicAdd(p.counter, 1ULL);
         }
         __syncthreads();
         const unsigned long long item = s_item;
-        __syncthreads();
         if (item >= nitems) break;
         const uint64_t seq = item / p.nseg;
         const uint32_t seg = (uint32_t)(item - seq * p.nseg);
         const uint32_t t0 = p.tile_prefix[seq], t1 = p.tile_prefix[seq + 1];
+        uint32_t *s_bits = tabs + (it & 1) * tabw;       // S / 32 bitmap words of the segment
+        uint32_t *s_pref = s_bits + S / 32;              // S / 64 running ranks, relative to the segment's first column
+        ++it;
         uint64_t col0, col1;   // columns of this segment
         if constexpr (CANON) {
-            const uint32_t wps = S / 32;   // bitmap words per segment
+            const uint32_t wps = S / 32;
             const uint32_t *gpref = p.rank_tab + p.tab_words;
             col0 = gpref[(size_t)seg * (wps / 2)];
             col1 = (seg + 1 < p.nseg) ? (uint64_t)gpref[(size_t)(seg + 1) * (wps / 2)] : p.dim;
@@ -286,20 +289,62 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
             col1 = min(p.dim, col0 + S);
         }
         const uint32_t bins = (uint32_t)(col1 - col0);   // multiple of 4 for every k this path serves (checked on the host)
-        if (bins == 0) continue;                         // uniform: a segment without canonical codes
-        for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) *reinterpret_cast<uint4 *>(hist + i) = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        // ---- count: one warp per run (the runs of this segment, one per tile of the sequence)
-        for (uint32_t t = t0 + warp; t < t1; t += CK_WARPS) {
-            const uint32_t rd = __ldg(p.runs + (uint64_t)t * p.nseg + seg);
-            const uint32_t cnt = rd & 0xFFFFu;
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)t * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3));
-            for (uint32_t i = lane; i * 8u < cnt; i += 32) {
-                const uint4 v = __ldg(src + i);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                const uint32_t left = cnt - i * 8u;
+        if (bins == 0) { __syncthreads(); continue; }    // uniform: a segment without canonical codes
+
+        for (uint32_t tp = t0; tp < t1 || tp == t0; tp += CK_MAXD) {   // (one pass even without tiles: zero row part)
+            // ---- descriptors of up to CK_MAXD runs, exclusive prefix of their unit counts (unit = 4 codes = 8 bytes)
+            const uint32_t nd = min((uint32_t)CK_MAXD, t1 - min(t1, tp));
+            uint32_t units = 0;
+            if ((uint32_t)tid < nd) {
+                const uint32_t rd = __ldg(p.runs + (uint64_t)(tp + tid) * p.nseg + seg);
+                s_len[tid] = rd & 0xFFFFu;
+                s_src[tid] = (tp + tid) * (uint32_t)(BK_TILE_CAP / 8) + (rd >> 16);
+                units = ((rd & 0xFFFFu) + 3u) >> 2;
+            }
+            uint32_t incl = units;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            uint32_t wbase = 0, total_units = 0;
+#pragma unroll
+            for (int w = 0; w < CK_WARPS; ++w) {
+                const uint32_t x = s_wsum[w];
+                if (w < warp) wbase += x;
+                total_units += x;
+            }
+            s_unit[tid] = wbase + incl - units;
+            if (tid == 0) s_unit[CK_MAXD] = total_units;
+            __syncthreads();
+            // unit u -> (run, 4 codes): binary search for the run, one 8-byte load
+            auto fetch = [&](uint32_t u, uint32_t &left) -> uint2 {
+                uint32_t lo = 0, hi = nd;   // largest r with s_unit[r] <= u
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (s_unit[mid] <= u) lo = mid; else hi = mid;
+                }
+                const uint32_t q = u - s_unit[lo];
+                left = s_len[lo] - 4u * q;
+                return __ldg(reinterpret_cast<const uint2 *>(p.pool + ((uint64_t)s_src[lo] << 3)) + q);
+            };
+            uint32_t left0 = 0;
+            uint2 first = make_uint2(0, 0);
+            if ((uint32_t)tid < total_units) first = fetch(tid, left0);
+            if (tp == t0) {   // first pass: the histogram must be free and zero
+                if (tid == 0 && in_flight) { bulk_wait_read(); in_flight = false; }
+                __syncthreads();
+                for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) *reinterpret_cast<uint4 *>(hist + i) = make_uint4(0, 0, 0, 0);
+                __syncthreads();
+            }
+            for (uint32_t u = tid; u < total_units; u += CK_THREADS) {
+                uint32_t left = left0;
+                const uint2 v = (u == (uint32_t)tid) ? first : fetch(u, left);
+                const uint32_t w[2] = {v.x, v.y};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
                     // (the padding behind a run is whatever the staging buffer held: keep it inside the tables)
                     const uint32_t e = ((q & 1) ? (w[q >> 1] >> 16) : w[q >> 1]) & (S - 1u);
                     uint32_t col = e;
@@ -313,8 +358,8 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
                     if ((uint32_t)q < left) atomicAdd(hist + col, 1u);
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
         const unsigned long long total = p.totals_in[seq];
         if (tid == 0 && seg == 0 && p.totals_out) p.totals_out[seq] = total;
         const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
@@ -342,12 +387,13 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
                 }
                 fence_async_smem();
                 __syncthreads();
-                if (tid == 0) bulk_store(row, hist, bins * 4u);
+                if (tid == 0) { bulk_store(row, hist, bins * 4u); in_flight = true; }
             } else {   // a part that does not start on a 16-byte boundary: plain coalesced stores
                 for (uint32_t i = tid; i < bins; i += CK_THREADS)
                     row[i] = small ? cvt_count<OUT, NORM, true>(hist[i], dF, rinv, dD) : cvt_count<OUT, NORM, false>(hist[i], dF, rinv, dD);
             }
         }
+        __syncthreads();   // everyone is done with s_item and the histogram of this item
     }
     if (tid == 0) bulk_wait_all();
 }

@@ -286,8 +286,10 @@ long FastxParser::fill(uint8_t *bases, size_t cap, size_t *used, std::vector<uin
                 return -1;
             }
         }
+        if (!err_.empty()) return -1;   // a read / inflate error ended the input early
         if (!commit()) return added;
     }
+    if (!err_.empty()) return -1;
     return added;
 }
 

@@ -270,6 +270,46 @@ int ktb_fastx_load(const char *path, int sniff, uint8_t **bases, uint64_t **offs
     return KTB_OK;
 }
 
+int ktb_debug_fastx_batches(const char *path, int sniff, uint64_t max_records, uint64_t batch_bytes, uint8_t **bases,
+                            uint64_t **offsets, uint64_t *n) {
+    if (!path || !bases || !offsets || !n || !max_records || !batch_bytes) return ktb_internal_fail(KTB_ERR_ARG, "bad argument");
+    *bases = nullptr; *offsets = nullptr; *n = 0;
+    ktb::ByteSource src;
+    std::string err;
+    if (!src.open(path, &err)) return ktb_internal_fail(KTB_ERR_IO, err.c_str());
+    ktb::SeqFormat fmt;
+    if (sniff) fmt = (src.peek_first_byte() == '>') ? ktb::SeqFormat::Fasta : ktb::SeqFormat::Fastq;
+    else if (!ktb::format_from_path(path, &fmt)) return ktb_internal_fail(KTB_ERR_IO, "unknown sequence file extension");
+    ktb::FastxParser parser(&src, fmt);
+    std::vector<uint8_t> all, buf(batch_bytes);
+    std::vector<uint64_t> all_offs{0}, offs;
+    for (;;) {   // the batch loop of run_file, with caller-chosen batch limits
+        offs.assign(1, 0);
+        size_t used = 0;
+        long got = 0;
+        for (;;) {
+            got = parser.fill(buf.data(), buf.size(), &used, &offs, (size_t)max_records);
+            if (got < 0) return ktb_internal_fail(KTB_ERR_IO, parser.error().c_str());
+            if (got == 0 && parser.need_bytes() && used == 0) {
+                buf.resize(parser.need_bytes() + 16);
+                continue;
+            }
+            break;
+        }
+        if (offs.size() == 1) break;
+        for (size_t i = 1; i < offs.size(); ++i) all_offs.push_back(all.size() + offs[i]);
+        all.insert(all.end(), buf.begin(), buf.begin() + used);
+        if (parser.eof()) break;
+    }
+    *n = all_offs.size() - 1;
+    *bases = (uint8_t *)malloc(all.size() ? all.size() : 1);
+    *offsets = (uint64_t *)malloc(all_offs.size() * 8);
+    if (!*bases || !*offsets) return ktb_internal_fail(KTB_ERR_NOMEM, "malloc failed");
+    if (!all.empty()) memcpy(*bases, all.data(), all.size());
+    memcpy(*offsets, all_offs.data(), all_offs.size() * 8);
+    return KTB_OK;
+}
+
 static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsize) {
     const bool cgr = cgr_vecsize > 0;
     const double t_start = now_ms();

@@ -174,9 +174,9 @@ __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hby
 }
 
 template <int OUT, bool NORM, int MODE, int NW>
-__global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW == 8 ? 4 : 8)) long_kernel(const LongParams p) {
+__global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 8)) long_kernel(const LongParams p) {
     static_assert(OUT == OUT_U32 || OUT == OUT_F32, "f64 rows keep seq_kernel");
-    static_assert(NW == 4 || NW == 8, "warps per CTA");
+    static_assert(NW == 4 || NW == 8 || NW == 10, "warps per CTA");
     extern __shared__ __align__(128) uint32_t lsm[];
     __shared__ unsigned long long s_item;
     __shared__ uint32_t s_total[2];
@@ -246,11 +246,14 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW == 8 ? 4 : 
                         if (near_end) return load16_guarded(p.bases, (cbase + c) << 4, p.total_bases);
                         return __ldg(seq_chunks + c);
                     };
+                    // two steps of bases in flight per warp (HBM latency is longer than one step of work at 24 warps/SM)
                     uint4 vnext = fetch(w0 + lane);
+                    uint4 vnext2 = fetch(w0 + 32 + lane);
                     for (uint32_t c0 = w0; c0 < w1; c0 += 32) {
                         const uint32_t c = c0 + lane;
                         const uint4 v = vnext;
-                        if (c0 + 32 < w1) vnext = fetch(c + 32);
+                        vnext = vnext2;
+                        if (c0 + 64 < w1) vnext2 = fetch(c + 64);
                         uint32_t cf, vm;
                         decode16(v, cf, vm);
                         if (c >= w1) { vm = 0; cf = (uint32_t)lane * 0x9E3779B1u; }   // idle lanes add 0 at scattered bins

@@ -29,6 +29,23 @@ def read_fastx(path: str | os.PathLike, sniff: bool = False) -> tuple[np.ndarray
     return bases, offsets
 
 
+def read_fastx_batched(path: str | os.PathLike, max_records: int, batch_bytes: int, sniff: bool = False):
+    """read_fastx through the drivers' batch loop with the given per-batch limits (test hook)."""
+    L = _lib.load()
+    pb, po, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    _lib.check(L.ktb_debug_fastx_batches(os.fsencode(str(path)), int(sniff), int(max_records), int(batch_bytes),
+                                         C.byref(pb), C.byref(po), C.byref(n)))
+    try:
+        offsets = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(n.value + 1,)).copy()
+        total = int(offsets[-1])
+        bases = (np.ctypeslib.as_array(C.cast(pb, C.POINTER(C.c_uint8)), shape=(total,)).copy() if total
+                 else np.zeros(0, dtype=np.uint8))
+    finally:
+        L.ktb_free(pb)
+        L.ktb_free(po)
+    return bases, offsets
+
+
 def comp_oligo(in_path, out_path, k: int = 3, counts: bool = False, raw_count: bool = False,
                preset: str = "spc", header: bool = False, threads: int = 0, device: int = 0) -> dict:
     """`kmertools comp oligo -i in -o out [-c] [-k K] [-r] [-p preset] [-H] [-t N]` on the GPU

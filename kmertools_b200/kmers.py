@@ -16,7 +16,7 @@ def kmer_pairs(seq, ksize: int, device: int = 0) -> tuple[np.ndarray, np.ndarray
     """(forward, reverse-complement) codes of every valid window of `seq`, in position order, as two uint64
     arrays.  `seq` is str / bytes / a uint8 array (ASCII or raw 0..3 codes, kmer/src/kmer.rs:6-15)."""
     if isinstance(seq, str):
-        seq = seq.encode("latin-1")
+        seq = seq.encode("utf-8")   # Rust's String::as_bytes (pybindings/src/kmer.rs:22-29), as OligoComputer does
     buf = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray, memoryview)) \
         else np.ascontiguousarray(seq, dtype=np.uint8)
     if not 1 <= int(ksize) <= 31:

@@ -13,6 +13,8 @@ def to_acgt(kmer: int, k: int) -> str:
 def to_numeric(kmer: str) -> tuple[int, int]:
     """kmer_to_numeric, kmer/src/lib.rs:36-50: (forward, reverse-complement) codes."""
     k = len(kmer)
+    if k > 32:   # the binding refuses what does not fit a u64 (pybindings/src/kmer.rs: "K-mer is too long")
+        raise ValueError("K-mer must be at most 32 bases long")
     mask = (1 << (2 * k)) - 1
     f = r = 0
     for ch in kmer:

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 from kmertools_b200._lib import NORM_CLI, NORM_COUNTS, NORM_PY  # noqa: E402
 
-TILE = 496 * 16   # bases per tile of bucket_kernel
+TILE = 248 * 16   # bases per tile of bucket_kernel
 
 
 @pytest.mark.parametrize("k,mins", [(9, True), (10, True), (8, False), (9, False)])
@@ -42,7 +42,7 @@ def test_bucket_segment_sizes(log2_seg):
     check(8, bases, offsets, mins=False, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"raw k8 seg 2^{log2_seg}",
           bucket_log2_seg=log2_seg)
     check(10, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"k10 seg 2^{log2_seg} (2^13: falls back)",
-          bucket_log2_seg=log2_seg, bucket_blocks=2)
+          bucket_log2_seg=log2_seg)
 
 
 def test_bucket_low_complexity_and_unaligned_starts():
@@ -60,7 +60,7 @@ def test_bucket_low_complexity_and_unaligned_starts():
 
 
 def test_bucket_one_long_contig():
-    """A 3 Mbp contig = 379 tiles of one sequence: count_kernel walks 379 runs per segment."""
+    """A 3 Mbp contig = 757 tiles of one sequence: count_kernel walks its runs in three passes of 256 descriptors."""
     rng = np.random.default_rng(5)
     bases, offsets = random_batch(rng, [700, 3_000_000, 0, 2500], noise=0.0005, n_runs=0.5)
     check(9, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what="k9 long contig")

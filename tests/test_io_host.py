@@ -77,3 +77,100 @@ def test_format6_is_correctly_rounded_half_even():
     cases += [k / 128 for k in range(129)] + [k / 2048 for k in range(0, 2049, 7)]
     for q in cases:
         assert kio.format6(float(q)) == "%.6f" % float(q), q
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Parser rules beyond the reference's own fixtures.  The reference reads records with rust-bio 2.3.0
+# (bio::io::fasta::Reader::read / bio::io::fastq::Reader::read, called through Records::next and unwrap()ed in
+# ktio/src/seq.rs:97-139) and inflates ".gz" with flate2::read::GzDecoder (seq.rs:149).  Neither crate is in
+# /root/reference and Rust cannot run here, so each case states the rule of the published source it restates.
+def _write(tmp_path, name, data):
+    p = tmp_path / name
+    p.write_bytes(data)
+    return p
+
+
+def test_fasta_crlf_and_blank_lines_inside_a_record(tmp_path):
+    # fasta::Reader::read: `record.seq.push_str(self.line.trim_end())` for every line up to the next '>' — CR, blanks
+    # and trailing spaces vanish, blank lines contribute nothing
+    p = _write(tmp_path, "a.fa", b">r1 desc\r\nACGT  \r\n\r\nTTGA\r\n\n>r2\nGG\n\n\n")
+    assert _as_list(*kio.read_fastx(p)) == [b"ACGTTTGA", b"GG"]
+
+
+def test_fasta_first_line_must_be_a_header(tmp_path):
+    # fasta::Reader::read: `if !self.line.starts_with('>') { Err("Expected > at record start.") }` — a blank FIRST line
+    # is not skipped (the reference then panics on unwrap)
+    from kmertools_b200 import KtbError
+    with pytest.raises(KtbError, match="Expected > at record start"):
+        kio.read_fastx(_write(tmp_path, "b.fa", b"\n>r1\nACGT\n"))
+
+
+def test_fasta_empty_record_ends_the_iteration(tmp_path):
+    # fasta::Records::next: `Ok(()) if record.is_empty() => None` — a bare ">" followed directly by another header
+    # (no id, no description, no sequence) stops the iteration, whatever follows; with an id the empty record counts
+    assert _as_list(*kio.read_fastx(_write(tmp_path, "c.fa", b">r1\nAC\n>\n>r3\nGG\n"))) == [b"AC"]
+    assert _as_list(*kio.read_fastx(_write(tmp_path, "d.fa", b">r1\nAC\n>r2\n>r3\nGG\n"))) == [b"AC", b"", b"GG"]
+    assert _as_list(*kio.read_fastx(_write(tmp_path, "e.fa", b">r1\nAC\n>\nTT\n>r3\nGG\n"))) == [b"AC", b"TT", b"GG"]
+
+
+def test_fasta_trailing_header_with_every_batch_boundary(tmp_path):
+    # a header as the LAST line (with and without a final newline) is a record with an empty sequence; batch limits
+    # must not lose it (the batch loop used to stop on end-of-input while that header was still pending)
+    for tail in (b">last\n", b">last"):
+        p = _write(tmp_path, "f.fa", b">r1\nACGT\n>r2\nGGA\nTT\n" + tail)
+        want = [b"ACGT", b"GGATT", b""]
+        assert _as_list(*kio.read_fastx(p)) == want
+        for max_records in (1, 2, 3):
+            for batch_bytes in (4, 5, 7, 64):
+                assert _as_list(*kio.read_fastx_batched(p, max_records, batch_bytes)) == want, (max_records, batch_bytes)
+
+
+def test_batch_boundaries_do_not_change_the_records(tmp_path):
+    rng = np.random.default_rng(11)
+    seqs = [bytes(rng.choice(list(b"ACGTN"), size=int(n)).astype(np.uint8)) for n in rng.integers(0, 200, size=60)]
+    fa = b"".join(b">s%d\n" % i + b"\n".join(s[j:j + 37] for j in range(0, len(s), 37)) + b"\n" for i, s in enumerate(seqs))
+    fq = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)) for i, s in enumerate(seqs) if s)
+    pa, pq = _write(tmp_path, "g.fa", fa), _write(tmp_path, "g.fq", fq)
+    for max_records, batch_bytes in ((1, 1 << 20), (7, 1 << 20), (1000, 64), (3, 150), (1000, 1)):
+        assert _as_list(*kio.read_fastx_batched(pa, max_records, batch_bytes)) == seqs
+        assert _as_list(*kio.read_fastx_batched(pq, max_records, batch_bytes)) == [s for s in seqs if s]
+
+
+def test_fastq_multiline_and_marker_characters_in_quality(tmp_path):
+    # fastq::Reader::read: sequence lines up to the first line starting with '+', then EXACTLY as many quality lines as
+    # there were sequence lines — so a quality line may start with '@', '+' or '>'
+    fq = b"@r1 d\nACGT\nTTGA\n+r1\n@III\n+>II\n@r2\nGG\n+\n>I\n"
+    assert _as_list(*kio.read_fastx(_write(tmp_path, "h.fq", fq))) == [b"ACGTTTGA", b"GG"]
+    # CRLF: trim_end on every line
+    assert _as_list(*kio.read_fastx(_write(tmp_path, "i.fq", fq.replace(b"\n", b"\r\n")))) == [b"ACGTTTGA", b"GG"]
+
+
+def test_fastq_errors_follow_the_reader(tmp_path):
+    from kmertools_b200 import KtbError
+    # Error::MissingAt for anything but '@' where a header is expected — including a blank line between records and a
+    # blank line at the end of the file (read_line returns "\n", which is not empty)
+    for data in (b"@r1\nAC\n+\nII\n\n@r2\nGG\n+\nII\n", b"@r1\nAC\n+\nII\n\n", b"r1\nAC\n+\nII\n"):
+        with pytest.raises(KtbError, match="Expected @ at record start"):
+            kio.read_fastx(_write(tmp_path, "j.fq", data))
+    # Error::IncompleteRecord when the quality string is empty: end of input before '+', no sequence line, blank quality
+    for data in (b"@r1\nACGT\n", b"@r1\n+\n", b"@r1\nAC\n+\n\n", b"@r1\nACGT"):
+        with pytest.raises(KtbError, match="Incomplete record"):
+            kio.read_fastx(_write(tmp_path, "k.fq", data))
+    # a missing final newline after a complete record is fine
+    assert _as_list(*kio.read_fastx(_write(tmp_path, "l.fq", b"@r1\nACGT\n+\nIIII"))) == [b"ACGT"]
+
+
+def test_gzip_only_the_first_member_is_read(tmp_path):
+    # flate2::read::GzDecoder decodes ONE member (MultiGzDecoder would continue); ktio/src/seq.rs:149 uses GzDecoder
+    m1 = gzip.compress(b">r1\nACGT\n>r2\nGG\n")
+    m2 = gzip.compress(b">r3\nTTTT\n")
+    assert _as_list(*kio.read_fastx(_write(tmp_path, "m.fa.gz", m1 + m2))) == [b"ACGT", b"GG"]
+    assert _as_list(*kio.read_fastx(_write(tmp_path, "n.fa.gz", m1))) == [b"ACGT", b"GG"]
+    big = b"".join(b">s%d\n%s\n" % (i, b"ACGTTGCA" * 200) for i in range(3000))       # several inflate calls
+    got = _as_list(*kio.read_fastx(_write(tmp_path, "o.fa.gz", gzip.compress(big) + m2)))
+    assert len(got) == 3000 and all(s == b"ACGTTGCA" * 200 for s in got)
+    from kmertools_b200 import KtbError
+    with pytest.raises(KtbError):   # a truncated member is an error, as it is for GzDecoder
+        kio.read_fastx(_write(tmp_path, "p.fa.gz", gzip.compress(big)[:-40]))
+    with pytest.raises(KtbError):   # ".gz" that is not gzip
+        kio.read_fastx(_write(tmp_path, "q.fa.gz", b">r1\nACGT\n"))
