@@ -150,9 +150,37 @@ int ktb_oligo_last_stats(const ktb_oligo *h, ktb_stats *out);
  *   "long_warps"         warps per CTA of long_kernel (0 = heuristic, 4 or 8) */
 int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value);
 
-/* Pinned host memory for callers that want asynchronous copies. */
+/* Pinned host memory for callers that want asynchronous copies (usable from every device).  ktb_host_alloc_near binds
+ * the pages to the NUMA node of `device` (from /sys/bus/pci/devices/<bdf>/numa_node; falls back to ktb_host_alloc when
+ * the topology is unknown), so that the copies of several GPUs do not all land on one node.  ktb_host_free frees both. */
 void *ktb_host_alloc(size_t bytes);
+void *ktb_host_alloc_near(size_t bytes, int device);
 void ktb_host_free(void *p);
+/* NUMA node of a CUDA device, -1 when unknown. */
+int ktb_device_numa_node(int device);
+
+/* ---- several GPUs, one call --------------------------------------------------------------------
+ * Replaces the reference's fan-out of ONE batch over all its workers with the row order kept
+ * (composition/src/oligo.rs:126-143 `buffer.par_iter().map(..).collect()`, pybindings/src/oligo.rs:77-81
+ * `seqs.into_par_iter()`): the batch is cut into one contiguous range of sequences per device, balanced by bases;
+ * every device computes its rows from its own host thread (one ktb_oligo handle, three stream sets per device) and
+ * writes its own slab of `out`.  Rows are independent: no collective.  ndev = 0 takes every visible device. */
+typedef struct ktb_multi ktb_multi;
+int ktb_multi_create(int k, const int *devices, int ndev, ktb_multi **out);
+void ktb_multi_destroy(ktb_multi *m);
+int ktb_multi_device_count(const ktb_multi *m);
+/* The per-device handle (for ktb_oligo_set_option / ktb_oligo_dim / ktb_oligo_header); owned by `m`. */
+ktb_oligo *ktb_multi_handle(ktb_multi *m, int i);
+/* Same contract as ktb_oligo_vectorise (host buffers). */
+int ktb_multi_vectorise(ktb_multi *m, const uint8_t *bases, const uint64_t *offsets, uint64_t n, int canonical,
+                        int norm_mode, int out_dtype, void *out, uint64_t *totals);
+/* Stats and row range [first_row, end_row) of device i in the most recent ktb_multi_vectorise. */
+int ktb_multi_last_stats(const ktb_multi *m, int i, ktb_stats *out, uint64_t *first_row, uint64_t *end_row);
+/* Page-locked n x dim output whose slab of device i lives on that device's NUMA node (release with ktb_host_free). */
+void *ktb_multi_alloc_rows(const ktb_multi *m, const uint64_t *offsets, uint64_t n, int canonical, int out_dtype);
+/* The partition itself: bounds[0..parts], part r = sequences [bounds[r], bounds[r+1]); cut r is the first sequence that
+ * starts at or after r/parts of the bases (by count when every sequence is empty).  Pure host arithmetic. */
+int ktb_shard_bounds(const uint64_t *offsets, uint64_t n, int parts, uint64_t *bounds);
 
 /* ---- file-level driver: `kmertools comp oligo` (kmertools/src/args.rs:70-103,242-263) ---------------
  * Replaces OligoComputer::{new, set_*, vectorise} (composition/src/oligo.rs:31-229): reads FASTA/FASTQ

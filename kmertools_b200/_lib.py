@@ -58,7 +58,17 @@ SYMBOLS = {
     "ktb_oligo_last_stats": (_I, [_VP, C.POINTER(Stats)]),
     "ktb_oligo_set_option": (_I, [_VP, C.c_char_p, C.c_int64]),
     "ktb_host_alloc": (_VP, [_SZ]),
+    "ktb_host_alloc_near": (_VP, [_SZ, _I]),
     "ktb_host_free": (None, [_VP]),
+    "ktb_device_numa_node": (_I, [_I]),
+    "ktb_multi_create": (_I, [_I, C.POINTER(_I), _I, C.POINTER(_VP)]),
+    "ktb_multi_destroy": (None, [_VP]),
+    "ktb_multi_device_count": (_I, [_VP]),
+    "ktb_multi_handle": (_VP, [_VP, _I]),
+    "ktb_multi_vectorise": (_I, [_VP, _VP, _VP, _U64, _I, _I, _I, _VP, _VP]),
+    "ktb_multi_last_stats": (_I, [_VP, _I, C.POINTER(Stats), C.POINTER(_U64), C.POINTER(_U64)]),
+    "ktb_multi_alloc_rows": (_VP, [_VP, _VP, _U64, _I, _I]),
+    "ktb_shard_bounds": (_I, [_VP, _U64, _I, _VP]),
     "ktb_comp_oligo_file": (_I, [C.POINTER(FileOpts), C.POINTER(FileStats)]),
     "ktb_comp_cgr_file": (_I, [C.POINTER(FileOpts), _I, C.POINTER(FileStats)]),
     "ktb_release_cached_buffers": (None, []),

@@ -5,6 +5,7 @@
 // per-sequence histogram + normalisation for a whole batch.  No CPU compute path exists here: without
 // a CUDA device every compute entry point returns KTB_ERR_NODEVICE.
 #include "../../include/kmertools_b200.h"
+#include "device_guard.h"
 #include "kernels.cuh"
 #include "long_kernel.cuh"
 #include "bucket_kernels.cuh"
@@ -16,6 +17,9 @@
 #include <cstring>
 #include <string>
 #include <vector>
+
+void ktb_internal_register_host(void *p, size_t bytes);   // multi.cu: registry of page-locked blocks
+void ktb_internal_free_host(void *p);
 
 namespace {
 
@@ -146,10 +150,11 @@ namespace {
 
 using namespace ktb;
 
-int set_device(const ktb_oligo *h) {
-    CU(cudaSetDevice(h->device));
-    return KTB_OK;
-}
+using ktb::DeviceGuard;
+#define ON_DEVICE(dev)                                                                              \
+    DeviceGuard device_guard_(dev);                                                                 \
+    if (device_guard_.err != cudaSuccess)                                                           \
+        return fail(KTB_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (int)(dev), cudaGetErrorString(device_guard_.err))
 
 template <typename K>
 int set_smem(K kern, size_t bytes) {
@@ -478,9 +483,11 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         uint32_t *tile_prefix = (uint32_t *)h->ws_tiles.p;
         TileInfo *tiles = (TileInfo *)((uint8_t *)h->ws_tiles.p + (((n + 1) * 4 + 63) & ~(uint64_t)63));
         CU(cudaMemsetAsync(h->d_counters + 8, 0, 3 * sizeof(unsigned long long), st));
-        tile_prefix_kernel<<<1, 1024, 0, st>>>(d_offsets, n, (uint32_t)h->k, tile_prefix, tiles);
+        tile_prefix_kernel<<<1, 1024, 0, st>>>(d_offsets, n, (uint32_t)h->k, tile_prefix);
+        tile_info_kernel<<<(unsigned)std::min<uint64_t>((ntiles_bound + 255) / 256, (uint64_t)h->sm_count * 8), 256, 0, st>>>(
+            d_offsets, n, tile_prefix, tiles);
         CU(cudaGetLastError());
-        h->stats.launches++;
+        h->stats.launches += 2;
         BucketParams bp{};
         bp.bases = d_bases; bp.n = n; bp.total_bases = total_bases;
         bp.tile_prefix = tile_prefix; bp.tiles = tiles;
@@ -507,11 +514,11 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
                 canonical ? (nrm ? count_kernel<OUT, true, true> : count_kernel<OUT, false, true>)
                           : (nrm ? count_kernel<OUT, true, false> : count_kernel<OUT, false, false>);
             const size_t S = (size_t)1 << log2_seg;
-            const size_t smem = (S + 2 * (S / 32 + S / 64)) * 4;
+            const size_t smem = (S + 2 * (S / 32)) * 4;
             if (int rc = set_smem(kern, smem)) return rc;
             int per_sm = 1;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CK_THREADS, smem));
-            const uint64_t grid = std::min<uint64_t>((uint64_t)h->sm_count * std::max(per_sm, 1), n * nseg);
+            const uint64_t grid = std::min<uint64_t>((uint64_t)h->sm_count * std::max(per_sm, 1), ((n + CK_SEQ_CHUNK - 1) / CK_SEQ_CHUNK) * nseg);
             kern<<<(unsigned)grid, CK_THREADS, smem, st>>>(cp);
             CU(cudaGetLastError());
             h->stats.launches++;
@@ -651,7 +658,7 @@ __attribute__((visibility("hidden"))) int ktb_internal_dispatch(ktb_oligo *h, co
                                                                uint64_t total_bases, int canonical, int norm_mode,
                                                                int out_dtype, void *d_out, uint64_t *d_totals,
                                                                cudaStream_t st) {
-    if (cudaSetDevice(h->device) != cudaSuccess) return fail(KTB_ERR_CUDA, "cudaSetDevice failed");
+    ON_DEVICE(h->device);
     return dispatch_device(h, d_bases, d_offsets, n, total_bases, canonical, norm_mode, out_dtype, d_out, d_totals, st);
 }
 __attribute__((visibility("hidden"))) int ktb_internal_fail(int code, const char *msg) { return fail(code, "%s", msg); }
@@ -731,7 +738,8 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
         ktb_oligo_destroy(h);
         return rc;
     };
-    if (int rc = set_device(h)) return bail(rc);
+    DeviceGuard device_guard_(device);
+    if (device_guard_.err != cudaSuccess) return bail(fail(KTB_ERR_CUDA, "cudaSetDevice(%d) failed", device));
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
         return bail(fail(KTB_ERR_CUDA, "cudaGetDeviceProperties failed"));
@@ -888,7 +896,7 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
 
 void ktb_oligo_destroy(ktb_oligo *h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard device_guard_(h->device);
     for (auto &s : h->sets) {
         if (s.stream) {
             cudaStreamSynchronize(s.stream);
@@ -1023,7 +1031,7 @@ int ktb_oligo_vectorise_device(ktb_oligo *h, const uint8_t *d_bases, const uint6
     if (total_bases && !d_bases) return fail(KTB_ERR_ARG, "null bases pointer");
     if (((uintptr_t)d_bases & 15) || ((uintptr_t)d_out & 15))
         return fail(KTB_ERR_ARG, "d_bases and d_out must be 16-byte aligned");
-    if (int rc = set_device(h)) return rc;
+    ON_DEVICE(h->device);
     h->stats = ktb_stats{};
     return dispatch_device(h, d_bases, d_offsets, n, total_bases, canonical, norm_mode, out_dtype, d_out,
                            d_totals, (cudaStream_t)stream);
@@ -1033,7 +1041,7 @@ int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offs
                         int norm_mode, int out_dtype, void *out, uint64_t *totals) {
     if (int rc = check_args(h, canonical, norm_mode, out_dtype)) return rc;
     if (n && (!offsets || !out)) return fail(KTB_ERR_ARG, "null pointer");
-    if (int rc = set_device(h)) return rc;
+    ON_DEVICE(h->device);
     const double t0 = now_ms();
     h->stats = ktb_stats{};
     if (n == 0) return KTB_OK;
@@ -1129,20 +1137,21 @@ int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offs
 
 void *ktb_host_alloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
         fail(KTB_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
+    ktb_internal_register_host(p, bytes);
     return p;
 }
 
 void ktb_host_free(void *p) {
-    if (p) cudaFreeHost(p);
+    if (p) ktb_internal_free_host(p);
 }
 
 int ktb_debug_nt4_table(ktb_oligo *h, uint8_t *out256) {
     if (!h || !out256) return fail(KTB_ERR_ARG, "null argument");
-    if (int rc = set_device(h)) return rc;
+    ON_DEVICE(h->device);
     uint8_t *d = nullptr;
     CU(cudaMalloc(&d, 256));
     ktb::nt4_table_kernel<<<1, 256>>>(d);

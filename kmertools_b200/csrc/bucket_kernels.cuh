@@ -35,7 +35,6 @@ constexpr int BK_MAX_SEG = 64;
 constexpr int BK_TILE_CAP = BK_TILE_CHUNKS * 16 + BK_MAX_SEG * 8;   // pool entries per tile (runs padded to 8 entries)
 constexpr int CK_THREADS = 256;              // count_kernel
 constexpr int CK_WARPS = CK_THREADS / 32;
-constexpr int CK_MAXD = 256;                 // run descriptors of one (sequence, segment) handled per pass
 
 // everything bucket_kernel needs to know about a tile, written once by tile_prefix_kernel (32 bytes = two 128-bit
 // loads that do not depend on each other, prefetched one tile ahead)
@@ -52,7 +51,7 @@ struct BucketParams {
     const uint32_t *tile_prefix;     // [n+1] exclusive prefix of tiles per sequence
     const TileInfo *tiles;           // [tile_prefix[n]]
     uint16_t *pool;                  // tile t owns entries [t * BK_TILE_CAP, (t+1) * BK_TILE_CAP)
-    uint32_t *runs;                  // [tile * nseg + seg] = (first entry of the run / 8) << 16 | count
+    uint32_t *runs;                  // [seg * ntiles + tile] = (first entry of the run / 8) << 16 | count
     unsigned long long *totals;      // [n] valid windows per sequence (zeroed)
     uint32_t k;
     uint32_t nseg;
@@ -65,8 +64,7 @@ __device__ __forceinline__ uint32_t bk_chunks(uint64_t a, uint64_t b, uint32_t k
 }
 
 // exclusive prefix of tiles per sequence; one CTA of 1024 threads, contiguous chunk of sequences per thread
-__global__ void __launch_bounds__(1024) tile_prefix_kernel(const uint64_t *offsets, uint64_t n, uint32_t k, uint32_t *tile_prefix,
-                                                           TileInfo *tiles) {
+__global__ void __launch_bounds__(1024) tile_prefix_kernel(const uint64_t *offsets, uint64_t n, uint32_t k, uint32_t *tile_prefix) {
     __shared__ uint32_t s_part[1024];
     const uint32_t tid = threadIdx.x;
     const uint64_t per = (n + 1023) / 1024;
@@ -87,16 +85,26 @@ __global__ void __launch_bounds__(1024) tile_prefix_kernel(const uint64_t *offse
     uint32_t run = s_part[tid] - sum;
     for (uint64_t i = lo; i < hi; ++i) {
         tile_prefix[i] = run;
-        const uint64_t q0 = offsets[i], q1 = offsets[i + 1];
-        const uint32_t nt = (bk_chunks(q0, q1, k) + BK_TILE_CHUNKS - 1) / BK_TILE_CHUNKS;
-        for (uint32_t t = 0; t < nt; ++t) {
-            TileInfo ti;
-            ti.q0 = q0; ti.q1 = q1; ti.seq = (uint32_t)i; ti.tile = t; ti.pad[0] = ti.pad[1] = 0;
-            tiles[run + t] = ti;
-        }
-        run += nt;
+        const uint32_t nch = bk_chunks(offsets[i], offsets[i + 1], k);
+        run += (nch + BK_TILE_CHUNKS - 1) / BK_TILE_CHUNKS;
     }
     if (tid == 1023) tile_prefix[n] = s_part[1023];
+}
+
+// one thread per tile: its sequence is the largest s with tile_prefix[s] <= tile
+__global__ void __launch_bounds__(256) tile_info_kernel(const uint64_t *offsets, uint64_t n, const uint32_t *tile_prefix, TileInfo *tiles) {
+    const uint32_t ntiles = tile_prefix[n];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
+        uint64_t lo = 0, hi = n;
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (tile_prefix[mid] <= t) lo = mid; else hi = mid;
+        }
+        TileInfo ti;
+        ti.q0 = offsets[lo]; ti.q1 = offsets[lo + 1]; ti.seq = (uint32_t)lo; ti.tile = t - tile_prefix[lo];
+        ti.pad[0] = ti.pad[1] = 0;
+        tiles[t] = ti;
+    }
 }
 
 template <bool CANON>
@@ -191,9 +199,9 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
                 if (lane >= d) incl += t;
             }
             const uint32_t b0 = incl - a0 - a1, b1 = b0 + a0;
-            uint32_t *rd = p.runs + tile_id * p.nseg;
-            if (2 * lane < (int)p.nseg) { s_base[2 * lane] = b0; rd[2 * lane] = ((b0 >> 3) << 16) | c0; }
-            if (2 * lane + 1 < (int)p.nseg) { s_base[2 * lane + 1] = b1; rd[2 * lane + 1] = ((b1 >> 3) << 16) | c1; }
+            uint32_t *rd = p.runs + tile_id;   // descriptors of one segment are contiguous over the tiles (count_kernel's order)
+            if (2 * lane < (int)p.nseg) { s_base[2 * lane] = b0; rd[(uint64_t)(2 * lane) * ntiles] = ((b0 >> 3) << 16) | c0; }
+            if (2 * lane + 1 < (int)p.nseg) { s_base[2 * lane + 1] = b1; rd[(uint64_t)(2 * lane + 1) * ntiles] = ((b1 >> 3) << 16) | c1; }
             if (lane == 31) s_copy = incl;
             if (lane == 0 && s_tot) atomicAdd(p.totals + ti.seq, (unsigned long long)s_tot);
         }
@@ -220,7 +228,7 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
 struct CountParams {
     const uint32_t *tile_prefix;   // [n+1]
     const uint16_t *pool;
-    const uint32_t *runs;
+    const uint32_t *runs;          // [seg * ntiles + tile]
     const unsigned long long *totals_in;   // [n] from bucket_kernel
     uint64_t *totals_out;          // optional
     void *out;
@@ -235,165 +243,142 @@ struct CountParams {
     int canonical;
 };
 
-// One CTA per (sequence, segment of the code space).  The columns of the segment are [R, R + bins): R = rank of the
-// segment's first code.  The runs of the segment (one per tile of the sequence) are flattened into units of four codes
-// and dealt to the threads, so all of them are in flight together; the first unit of every thread, the descriptors and
-// the segment's rank tables are loaded BEFORE the CTA waits for the bulk copy of its previous part to leave the
-// histogram, so the two latencies overlap.  u32 / f32 parts leave as one bulk copy, f64 parts are stored directly.
+constexpr int CK_SEQ_CHUNK = 8;   // consecutive sequences that share one load of a segment's rank tables
+
+// One CTA per (segment of the code space, chunk of CK_SEQ_CHUNK sequences).  The columns of the segment are
+// [R, R + bins): R = rank of the segment's first code.  For every sequence of the chunk the runs of the segment (one
+// per tile of the sequence, contiguous descriptors) are dealt to HALF-WARPS — a run of ~60 codes is 15 eight-byte
+// loads — counted with shared-memory atomics and written out as one bulk copy (u32 / f32; f64 parts are stored
+// directly).  The first run of every half-warp is loaded BEFORE the CTA waits for the bulk copy of the previous part
+// to leave the histogram, so that latency and the copy overlap.
 template <int OUT, bool NORM, bool CANON>
 __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams p) {
     extern __shared__ __align__(128) uint32_t csm[];
-    __shared__ unsigned long long s_item;
-    __shared__ uint32_t s_unit[CK_MAXD + 1];   // exclusive prefix of the runs' unit counts
-    __shared__ uint32_t s_src[CK_MAXD];        // first pool entry of the run / 8
-    __shared__ uint32_t s_len[CK_MAXD];        // codes in the run
-    __shared__ uint32_t s_wsum[CK_WARPS];
+    __shared__ unsigned long long s_unit;
     using T = typename OutT<OUT>::type;
     const uint32_t S = 1u << p.log2_seg;                 // codes per segment
-    const uint32_t tabw = S / 32 + S / 64;               // words of one copy of the segment's rank tables
+    const uint32_t wps = S / 32;                         // bitmap words per segment
     uint32_t *hist = csm;                                // up to S bins
-    uint32_t *tabs = csm + S;                            // CANON: two copies (items alternate)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr uint32_t FULL = 0xffffffffu;
-    const uint64_t nitems = p.n * p.nseg;
-    // items differ in cost (segments hold between none and twice the average number of k-mers), so they are dealt out
-    // dynamically; the counter is read one item ahead to keep its round trip off the critical path
-    unsigned long long next_item = 0;
-    if (tid == 0) next_item = atomicAdd(p.counter, 1ULL);
-    uint32_t it = 0;
+    uint32_t *s_bits = csm + S;                          // CANON: bitmap of the segment's canonical codes
+    uint32_t *s_pref = s_bits + wps;                     // CANON: columns before each word, relative to the segment's first
+    const int tid = threadIdx.x;
+    const uint32_t hw = tid >> 4, hl = tid & 15;         // half-warp, lane in it
+    constexpr uint32_t NHW = CK_THREADS / 16;
+    const uint32_t ntiles = p.tile_prefix[p.n];
+    const uint64_t nchunks = (p.n + CK_SEQ_CHUNK - 1) / CK_SEQ_CHUNK;
+    const uint64_t nunits = nchunks * p.nseg;
+    // units differ in cost (segments hold between none and twice the average number of k-mers), so they are dealt out
+    // dynamically; the counter is read one unit ahead to keep its round trip off the critical path
+    unsigned long long next_unit = 0;
+    if (tid == 0) next_unit = atomicAdd(p.counter, 1ULL);
     bool in_flight = false;   // (tid 0) a bulk copy out of `hist` may still be reading it
     for (;;) {
+        __syncthreads();      // everyone is done with s_unit and the tables of the previous unit
         if (tid == 0) {
-            s_item = next_item;
-            next_item = atomicAdd(p.counter, 1ULL);
+            s_unit = next_unit;
+            next_unit = atomicAdd(p.counter, 1ULL);
         }
         __syncthreads();
-        const unsigned long long item = s_item;
-        if (item >= nitems) break;
-        const uint64_t seq = item / p.nseg;
-        const uint32_t seg = (uint32_t)(item - seq * p.nseg);
-        const uint32_t t0 = p.tile_prefix[seq], t1 = p.tile_prefix[seq + 1];
-        uint32_t *s_bits = tabs + (it & 1) * tabw;       // S / 32 bitmap words of the segment
-        uint32_t *s_pref = s_bits + S / 32;              // S / 64 running ranks, relative to the segment's first column
-        ++it;
+        const unsigned long long unit = s_unit;
+        if (unit >= nunits) break;
+        const uint64_t chunk = unit / p.nseg;
+        const uint32_t seg = (uint32_t)(unit - chunk * p.nseg);
         uint64_t col0, col1;   // columns of this segment
         if constexpr (CANON) {
-            const uint32_t wps = S / 32;
             const uint32_t *gpref = p.rank_tab + p.tab_words;
             col0 = gpref[(size_t)seg * (wps / 2)];
             col1 = (seg + 1 < p.nseg) ? (uint64_t)gpref[(size_t)(seg + 1) * (wps / 2)] : p.dim;
-            for (uint32_t i = tid; i < wps; i += CK_THREADS) s_bits[i] = __ldg(p.rank_tab + (size_t)seg * wps + i);
-            for (uint32_t i = tid; i < wps / 2; i += CK_THREADS) s_pref[i] = __ldg(gpref + (size_t)seg * (wps / 2) + i) - (uint32_t)col0;
+            for (uint32_t w = tid; w < wps; w += CK_THREADS) {
+                const uint32_t bits = __ldg(p.rank_tab + (size_t)seg * wps + w);
+                const uint32_t prev = (w & 1u) ? __ldg(p.rank_tab + (size_t)seg * wps + w - 1) : 0u;
+                s_bits[w] = bits;
+                s_pref[w] = __ldg(gpref + ((size_t)seg * wps + w) / 2) - (uint32_t)col0 + (uint32_t)__popc(prev);
+            }
         } else {
             col0 = (uint64_t)seg * S;
             col1 = min(p.dim, col0 + S);
         }
         const uint32_t bins = (uint32_t)(col1 - col0);   // multiple of 4 for every k this path serves (checked on the host)
-        if (bins == 0) { __syncthreads(); continue; }    // uniform: a segment without canonical codes
-
-        for (uint32_t tp = t0; tp < t1 || tp == t0; tp += CK_MAXD) {   // (one pass even without tiles: zero row part)
-            // ---- descriptors of up to CK_MAXD runs, exclusive prefix of their unit counts (unit = 4 codes = 8 bytes)
-            const uint32_t nd = min((uint32_t)CK_MAXD, t1 - min(t1, tp));
-            uint32_t units = 0;
-            if ((uint32_t)tid < nd) {
-                const uint32_t rd = __ldg(p.runs + (uint64_t)(tp + tid) * p.nseg + seg);
-                s_len[tid] = rd & 0xFFFFu;
-                s_src[tid] = (tp + tid) * (uint32_t)(BK_TILE_CAP / 8) + (rd >> 16);
-                units = ((rd & 0xFFFFu) + 3u) >> 2;
+        if (bins == 0) continue;                         // uniform: a segment without canonical codes
+        const uint32_t *runs = p.runs + (uint64_t)seg * ntiles;
+        const uint64_t seq_end = min(p.n, (chunk + 1) * CK_SEQ_CHUNK);
+        for (uint64_t seq = chunk * CK_SEQ_CHUNK; seq < seq_end; ++seq) {
+            const uint32_t t0 = p.tile_prefix[seq], t1 = p.tile_prefix[seq + 1];
+            // ---- first run of this half-warp: descriptor and first eight bytes per lane, before the histogram is free
+            uint32_t r = t0 + hw, cnt = 0;
+            const uint2 *src = nullptr;
+            uint2 v = make_uint2(0, 0);
+            if (r < t1) {
+                const uint32_t rd = __ldg(runs + r);
+                cnt = rd & 0xFFFFu;
+                src = reinterpret_cast<const uint2 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3));
+                if (4u * hl < cnt) v = __ldg(src + hl);
             }
-            uint32_t incl = units;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(FULL, incl, d);
-                if (lane >= d) incl += t;
-            }
-            if (lane == 31) s_wsum[warp] = incl;
+            if (tid == 0 && in_flight) { bulk_wait_read(); in_flight = false; }
+            __syncthreads();   // (also: the rank tables of this unit are complete)
+            for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) *reinterpret_cast<uint4 *>(hist + i) = make_uint4(0, 0, 0, 0);
             __syncthreads();
-            uint32_t wbase = 0, total_units = 0;
+            // ---- count
+            while (r < t1) {
+                for (uint32_t q = hl; 4u * q < cnt; q += 16) {
+                    if (q != hl) v = __ldg(src + q);
+                    const uint32_t left = cnt - 4u * q;
+                    const uint32_t w[2] = {v.x, v.y};
 #pragma unroll
-            for (int w = 0; w < CK_WARPS; ++w) {
-                const uint32_t x = s_wsum[w];
-                if (w < warp) wbase += x;
-                total_units += x;
-            }
-            s_unit[tid] = wbase + incl - units;
-            if (tid == 0) s_unit[CK_MAXD] = total_units;
-            __syncthreads();
-            // unit u -> (run, 4 codes): binary search for the run, one 8-byte load
-            auto fetch = [&](uint32_t u, uint32_t &left) -> uint2 {
-                uint32_t lo = 0, hi = nd;   // largest r with s_unit[r] <= u
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (s_unit[mid] <= u) lo = mid; else hi = mid;
-                }
-                const uint32_t q = u - s_unit[lo];
-                left = s_len[lo] - 4u * q;
-                return __ldg(reinterpret_cast<const uint2 *>(p.pool + ((uint64_t)s_src[lo] << 3)) + q);
-            };
-            uint32_t left0 = 0;
-            uint2 first = make_uint2(0, 0);
-            if ((uint32_t)tid < total_units) first = fetch(tid, left0);
-            if (tp == t0) {   // first pass: the histogram must be free and zero
-                if (tid == 0 && in_flight) { bulk_wait_read(); in_flight = false; }
-                __syncthreads();
-                for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) *reinterpret_cast<uint4 *>(hist + i) = make_uint4(0, 0, 0, 0);
-                __syncthreads();
-            }
-            for (uint32_t u = tid; u < total_units; u += CK_THREADS) {
-                uint32_t left = left0;
-                const uint2 v = (u == (uint32_t)tid) ? first : fetch(u, left);
-                const uint32_t w[2] = {v.x, v.y};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    // (the padding behind a run is whatever the staging buffer held: keep it inside the tables)
-                    const uint32_t e = ((q & 1) ? (w[q >> 1] >> 16) : w[q >> 1]) & (S - 1u);
-                    uint32_t col = e;
-                    if constexpr (CANON) {
-                        const uint32_t wd = e >> 5;
-                        const uint2 bw = reinterpret_cast<const uint2 *>(s_bits)[wd >> 1];
-                        const bool odd = (wd & 1u) != 0u;
-                        const uint32_t below = (odd ? bw.y : bw.x) & ((1u << (e & 31u)) - 1u);
-                        col = s_pref[wd >> 1] + (uint32_t)__popc(below) + (odd ? (uint32_t)__popc(bw.x) : 0u);
-                    }
-                    if ((uint32_t)q < left) atomicAdd(hist + col, 1u);
-                }
-            }
-            __syncthreads();
-        }
-        const unsigned long long total = p.totals_in[seq];
-        if (tid == 0 && seg == 0 && p.totals_out) p.totals_out[seq] = total;
-        const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
-        const float dF = (float)dv, rinv = __frcp_rn(dF);
-        const double dD = (double)dv;
-        const bool small = dv < (1ULL << 23);
-        T *row = reinterpret_cast<T *>(p.out) + seq * p.dim + col0;
-        if constexpr (OUT == OUT_F64) {
-            for (uint32_t i = tid; i < bins; i += CK_THREADS) row[i] = cvt_count<OUT_F64, NORM, false>(hist[i], dF, rinv, dD);
-        } else {
-            if ((reinterpret_cast<uintptr_t>(row) & 15) == 0 && (bins & 3) == 0) {
-                if constexpr (OUT == OUT_F32) {   // counts -> floats in place
-                    for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) {
-                        const uint4 c = *reinterpret_cast<const uint4 *>(hist + i);
-                        float4 o;
-                        if (small) {
-                            o.x = cvt_count<OUT_F32, NORM, true>(c.x, dF, rinv, dD); o.y = cvt_count<OUT_F32, NORM, true>(c.y, dF, rinv, dD);
-                            o.z = cvt_count<OUT_F32, NORM, true>(c.z, dF, rinv, dD); o.w = cvt_count<OUT_F32, NORM, true>(c.w, dF, rinv, dD);
-                        } else {
-                            o.x = cvt_count<OUT_F32, NORM, false>(c.x, dF, rinv, dD); o.y = cvt_count<OUT_F32, NORM, false>(c.y, dF, rinv, dD);
-                            o.z = cvt_count<OUT_F32, NORM, false>(c.z, dF, rinv, dD); o.w = cvt_count<OUT_F32, NORM, false>(c.w, dF, rinv, dD);
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const uint32_t e = (e4 & 1) ? (w[e4 >> 1] >> 16) : (w[e4 >> 1] & 0xFFFFu);
+                        uint32_t col = e;
+                        if constexpr (CANON) {
+                            const uint32_t wd = (e >> 5) & (wps - 1u);   // (padding behind a run is arbitrary: stay inside the tables)
+                            col = s_pref[wd] + (uint32_t)__popc(s_bits[wd] & ~(0xFFFFFFFFu << (e & 31u)));
                         }
-                        *reinterpret_cast<float4 *>(hist + i) = o;
+                        if ((uint32_t)e4 < left) atomicAdd(hist + col, 1u);
                     }
                 }
-                fence_async_smem();
-                __syncthreads();
-                if (tid == 0) { bulk_store(row, hist, bins * 4u); in_flight = true; }
-            } else {   // a part that does not start on a 16-byte boundary: plain coalesced stores
-                for (uint32_t i = tid; i < bins; i += CK_THREADS)
-                    row[i] = small ? cvt_count<OUT, NORM, true>(hist[i], dF, rinv, dD) : cvt_count<OUT, NORM, false>(hist[i], dF, rinv, dD);
+                r += NHW;
+                if (r < t1) {
+                    const uint32_t rd = __ldg(runs + r);
+                    cnt = rd & 0xFFFFu;
+                    src = reinterpret_cast<const uint2 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3));
+                    if (4u * hl < cnt) v = __ldg(src + hl);
+                }
+            }
+            __syncthreads();
+            // ---- normalise and write this part of the row
+            const unsigned long long total = p.totals_in[seq];
+            if (tid == 0 && seg == 0 && p.totals_out) p.totals_out[seq] = total;
+            const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
+            const float dF = (float)dv, rinv = __frcp_rn(dF);
+            const double dD = (double)dv;
+            const bool small = dv < (1ULL << 23);
+            T *row = reinterpret_cast<T *>(p.out) + seq * p.dim + col0;
+            if constexpr (OUT == OUT_F64) {
+                for (uint32_t i = tid; i < bins; i += CK_THREADS) row[i] = cvt_count<OUT_F64, NORM, false>(hist[i], dF, rinv, dD);
+            } else {
+                if ((reinterpret_cast<uintptr_t>(row) & 15) == 0 && (bins & 3) == 0) {
+                    if constexpr (OUT == OUT_F32) {   // counts -> floats in place
+                        for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) {
+                            const uint4 c = *reinterpret_cast<const uint4 *>(hist + i);
+                            float4 o;
+                            if (small) {
+                                o.x = cvt_count<OUT_F32, NORM, true>(c.x, dF, rinv, dD); o.y = cvt_count<OUT_F32, NORM, true>(c.y, dF, rinv, dD);
+                                o.z = cvt_count<OUT_F32, NORM, true>(c.z, dF, rinv, dD); o.w = cvt_count<OUT_F32, NORM, true>(c.w, dF, rinv, dD);
+                            } else {
+                                o.x = cvt_count<OUT_F32, NORM, false>(c.x, dF, rinv, dD); o.y = cvt_count<OUT_F32, NORM, false>(c.y, dF, rinv, dD);
+                                o.z = cvt_count<OUT_F32, NORM, false>(c.z, dF, rinv, dD); o.w = cvt_count<OUT_F32, NORM, false>(c.w, dF, rinv, dD);
+                            }
+                            *reinterpret_cast<float4 *>(hist + i) = o;
+                        }
+                    }
+                    fence_async_smem();
+                    __syncthreads();
+                    if (tid == 0) { bulk_store(row, hist, bins * 4u); in_flight = true; }
+                } else {   // a part that does not start on a 16-byte boundary: plain coalesced stores
+                    for (uint32_t i = tid; i < bins; i += CK_THREADS)
+                        row[i] = small ? cvt_count<OUT, NORM, true>(hist[i], dF, rinv, dD) : cvt_count<OUT, NORM, false>(hist[i], dF, rinv, dD);
+                }
             }
         }
-        __syncthreads();   // everyone is done with s_item and the histogram of this item
     }
     if (tid == 0) bulk_wait_all();
 }

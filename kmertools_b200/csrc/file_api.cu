@@ -4,6 +4,7 @@
 // asynchronous writer (span_writer.h: `-t` threads copy disjoint spans into a shared mapping of the output, as the
 // reference's mmap writer does), so writing batch b also overlaps batch b+1.  Device side: counts + format_norm_kernel.
 #include "../../include/kmertools_b200.h"
+#include "device_guard.h"
 #include "fastx.h"
 #include "span_writer.h"
 #include "textfmt.cuh"
@@ -333,6 +334,8 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
     ktb_oligo *h = nullptr;
     if (int rc = ktb_oligo_create(o->k, o->device, &h)) return rc;
     struct Guard { ktb_oligo *h; ~Guard() { ktb_oligo_destroy(h); } } guard{h};
+    ktb::DeviceGuard device_guard(o->device);   // buffers and streams of this run live on the handle's device
+    if (device_guard.err != cudaSuccess) return ktb_internal_fail(KTB_ERR_CUDA, "cudaSetDevice failed");
     const uint64_t dim = ktb_oligo_dim(h, cgr ? 1 : o->canonical);
 
     // `-t` (kmertools/src/args.rs:249-251; 0 = all cores): threads of the output writer and of the host formatter
@@ -531,7 +534,7 @@ void ktb_release_cached_buffers(void) {
         g_pool = nullptr;
     }
     if (old) {
-        cudaSetDevice(old->device);
+        ktb::DeviceGuard device_guard(old->device);
         delete old;
     }
 }

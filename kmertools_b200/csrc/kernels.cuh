@@ -860,11 +860,18 @@ __device__ __forceinline__ float4 wave_cvt4(const WaveParams &p, uint4 c, unsign
     const float dF = (float)dv, rinv = __frcp_rn(dF);
     const double dD = (double)dv;
     float4 o;
-    if (!norm) {
-        o.x = cvt_count<OUT_F32, false, true>(c.x, dF, rinv, dD);
-        o.y = cvt_count<OUT_F32, false, true>(c.y, dF, rinv, dD);
-        o.z = cvt_count<OUT_F32, false, true>(c.z, dF, rinv, dD);
-        o.w = cvt_count<OUT_F32, false, true>(c.w, dF, rinv, dD);
+    if (!norm) {   // a count is at most `total`: the magic-constant conversion is exact below 2^23
+        if (total < (1ULL << 23)) {
+            o.x = cvt_count<OUT_F32, false, true>(c.x, dF, rinv, dD);
+            o.y = cvt_count<OUT_F32, false, true>(c.y, dF, rinv, dD);
+            o.z = cvt_count<OUT_F32, false, true>(c.z, dF, rinv, dD);
+            o.w = cvt_count<OUT_F32, false, true>(c.w, dF, rinv, dD);
+        } else {
+            o.x = cvt_count<OUT_F32, false, false>(c.x, dF, rinv, dD);
+            o.y = cvt_count<OUT_F32, false, false>(c.y, dF, rinv, dD);
+            o.z = cvt_count<OUT_F32, false, false>(c.z, dF, rinv, dD);
+            o.w = cvt_count<OUT_F32, false, false>(c.w, dF, rinv, dD);
+        }
     } else if (dv < (1ULL << 23)) {
         o.x = cvt_count<OUT_F32, true, true>(c.x, dF, rinv, dD);
         o.y = cvt_count<OUT_F32, true, true>(c.y, dF, rinv, dD);

@@ -6,6 +6,7 @@
 // before its span without carrying state.  Three launches: count per block, scan of the block counts, write.
 // Output-bound (16 bytes per k-mer against 1 byte per base), so the spans are short and re-derived rather
 // than staged.
+#include "device_guard.h"
 #include "../../include/kmertools_b200.h"
 
 #include <cuda_runtime.h>
@@ -185,7 +186,8 @@ int ktb_kmer_pairs(const uint8_t *seq, uint64_t len, int k, int device, uint64_t
     const int ndev = ktb_device_count();
     if (ndev <= 0) return ktb_internal_fail(KTB_ERR_NODEVICE, "no CUDA device available (this library has no CPU path)");
     if (device < 0 || device >= ndev) return ktb_internal_fail(KTB_ERR_ARG, "device out of range");
-    CUP(cudaSetDevice(device));
+    ktb::DeviceGuard device_guard(device);
+    CUP(device_guard.err);
     *count = 0;
     if (len < (uint64_t)k) return KTB_OK;
     const uint64_t max_pairs = len - (uint64_t)k + 1;

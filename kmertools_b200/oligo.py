@@ -187,3 +187,109 @@ class OligoComputer:
         """Device-pointer entry point (raw addresses, e.g. torch.Tensor.data_ptr()); asynchronous."""
         _lib.check(self._lib.ktb_oligo_vectorise_device(self._h, d_bases, d_offsets, n, total_bases, int(mins),
                                                         int(norm_mode), int(out_dtype), d_out, d_totals, stream))
+
+
+class MultiOligoComputer:
+    """All GPUs of the box behind one call (ktb_multi_*, csrc/multi.cu): the batch is cut into one contiguous range
+    of sequences per device, balanced by bases; every device writes its own slab of rows; row order = input order,
+    like the reference's rayon fan-out (pybindings/src/oligo.rs:77-81).  devices=None takes every visible GPU."""
+
+    def __init__(self, ksize: int, devices: Sequence[int] | None = None):
+        self._lib = _lib.load()
+        self.ksize = int(ksize)
+        devs = list(devices) if devices is not None else []
+        arr = (C.c_int * max(1, len(devs)))(*devs)
+        m = C.c_void_p()
+        _lib.check(self._lib.ktb_multi_create(self.ksize, arr, len(devs), C.byref(m)))
+        self._m = m
+        self.ndev = int(self._lib.ktb_multi_device_count(m))
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.ktb_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def dim(self, mins: bool = True) -> int:
+        return int(self._lib.ktb_oligo_dim(self._lib.ktb_multi_handle(self._m, 0), int(mins)))
+
+    def set_option(self, key: str, value: int) -> None:
+        for i in range(self.ndev):
+            _lib.check(self._lib.ktb_oligo_set_option(self._lib.ktb_multi_handle(self._m, i), key.encode(), int(value)))
+
+    def alloc_rows(self, offsets: np.ndarray, mins: bool = True, dtype=np.float32) -> "HostRows":
+        """Page-locked (n, dim) output whose slab of device i lives on that device's NUMA node."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        return HostRows(self, offsets, mins, dtype)
+
+    def vectorise_packed(self, bases: np.ndarray, offsets: np.ndarray, norm_mode: int = NORM_CLI, mins: bool = True,
+                         dtype=np.float32, out: np.ndarray | None = None, totals: np.ndarray | None = None) -> np.ndarray:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        d = self.dim(mins)
+        code = _CODES[np.dtype(dtype)]
+        if out is None:
+            out = np.empty((n, d), dtype=_DTYPES[code])
+        assert out.shape == (n, d) and out.dtype == _DTYPES[code] and out.flags.c_contiguous
+        tptr = None
+        if totals is not None:
+            assert totals.dtype == np.uint64 and totals.shape == (n,) and totals.flags.c_contiguous
+            tptr = totals.ctypes.data
+        _lib.check(self._lib.ktb_multi_vectorise(self._m, bases.ctypes.data if bases.size else None, offsets.ctypes.data, n,
+                                                 int(mins), int(norm_mode), code, out.ctypes.data if n else None, tptr))
+        return out
+
+    def vectorise_batch(self, seqs: Iterable[str], norm: bool = True, mins: bool = True) -> list[list[float]]:
+        """Reference semantics (pybindings/src/oligo.rs:77-81) over all devices."""
+        bases, offsets = _pack(list(seqs))
+        return self.vectorise_packed(bases, offsets, NORM_PY if norm else NORM_COUNTS, mins, np.float64).tolist()
+
+    def device_stats(self, i: int) -> dict:
+        st = _lib.Stats()
+        lo, hi = C.c_uint64(), C.c_uint64()
+        _lib.check(self._lib.ktb_multi_last_stats(self._m, int(i), C.byref(st), C.byref(lo), C.byref(hi)))
+        d = {f: getattr(st, f) for f, _ in st._fields_}
+        d.update(first_row=int(lo.value), end_row=int(hi.value))
+        return d
+
+
+class HostRows:
+    """Output buffer from ktb_multi_alloc_rows, viewed as a numpy array."""
+
+    def __init__(self, multi: MultiOligoComputer, offsets: np.ndarray, mins: bool, dtype):
+        self._lib = multi._lib
+        n = len(offsets) - 1
+        code = _CODES[np.dtype(dtype)]
+        d = multi.dim(mins)
+        self.ptr = self._lib.ktb_multi_alloc_rows(multi._m, offsets.ctypes.data, n, int(mins), code)
+        if not self.ptr:
+            _lib.check(_lib.KTB_ERR_NOMEM)
+        nbytes = max(1, n * d * np.dtype(dtype).itemsize)
+        buf = (C.c_uint8 * nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=_DTYPES[code], count=n * d).reshape(n, d)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.ktb_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def shard_bounds(offsets: np.ndarray, parts: int) -> np.ndarray:
+    """bounds[0..parts] of the library's partition (ktb_shard_bounds): part r = sequences [bounds[r], bounds[r+1])."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    out = np.zeros(int(parts) + 1, dtype=np.uint64)
+    _lib.check(_lib.load().ktb_shard_bounds(offsets.ctypes.data, len(offsets) - 1, int(parts), out.ctypes.data))
+    return out

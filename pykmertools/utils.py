@@ -13,12 +13,12 @@ def to_acgt(kmer: int, k: int) -> str:
 def to_numeric(kmer: str) -> tuple[int, int]:
     """kmer_to_numeric, kmer/src/lib.rs:36-50: (forward, reverse-complement) codes."""
     k = len(kmer)
-    if k > 32:   # the binding refuses what does not fit a u64 (pybindings/src/kmer.rs: "K-mer is too long")
-        raise ValueError("K-mer must be at most 32 bases long")
+    if k > 32:   # pybindings/src/kmer.rs:57-63 (a u64 holds 32 bases)
+        raise ValueError(f"Invalid k-mer length: {k}, must be <= 32")
     mask = (1 << (2 * k)) - 1
     f = r = 0
     for ch in kmer:
         c = _C.get(ch, 4)
         f = ((f << 2) | c) & mask
         r = (r >> 2) | ((c ^ 3) << (2 * (k - 1)))
-    return f, r
+    return f & 0xFFFFFFFFFFFFFFFF, r & 0xFFFFFFFFFFFFFFFF

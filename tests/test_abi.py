@@ -77,3 +77,6 @@ def test_utils_mirror():  # tests/test_utils.py of the reference
     from pykmertools import utils
     assert utils.to_acgt(111, 5) == "ACGTT"
     assert utils.to_numeric("ACGTT") == (111, 27)
+    assert utils.to_numeric("T" * 32) == (2 ** 64 - 1, 0)
+    with pytest.raises(ValueError, match="Invalid k-mer length: 33, must be <= 32"):   # pybindings/src/kmer.rs:57-63
+        utils.to_numeric("A" * 33)

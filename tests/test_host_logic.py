@@ -27,3 +27,26 @@ def test_pack_helper_matches_oracle_pack():
     b1, o1 = _pack(seqs)
     b2, o2 = O.pack([s.encode() for s in seqs])
     assert np.array_equal(b1, b2) and np.array_equal(o1, o2)
+
+
+def test_shard_bounds_matches_the_python_sharder():
+    """ktb_shard_bounds (the product's partition, csrc/multi.cu) == kmertools_b200.shard.shard_by_bases: contiguous,
+    complete, monotone, balanced by bases; by count when every sequence is empty."""
+    from kmertools_b200 import shard_bounds
+    from kmertools_b200.shard import shard_by_bases
+    from tests.util import random_batch
+    rng = np.random.default_rng(5)
+    cases = [rng.integers(0, 400, size=300), np.r_[rng.integers(0, 50, size=40), [90_000], rng.integers(0, 50, size=40)],
+             np.zeros(17, dtype=np.int64), np.array([5]), np.array([], dtype=np.int64), np.full(1000, 150)]
+    for lengths in cases:
+        _, offsets = random_batch(rng, lengths)
+        for shift in (0, 37):
+            offs = offsets + np.uint64(shift)
+            for parts in (1, 2, 3, 8):
+                b = shard_bounds(offs, parts)
+                assert b[0] == 0 and b[-1] == len(lengths) and np.all(np.diff(b.astype(np.int64)) >= 0)
+                for r in range(parts):
+                    assert (int(b[r]), int(b[r + 1])) == shard_by_bases(offs, parts, r)
+                if len(lengths) and lengths.sum():
+                    per = [int(offs[b[r + 1]]) - int(offs[b[r]]) for r in range(parts)]
+                    assert max(per) - lengths.sum() / parts <= lengths.max()
