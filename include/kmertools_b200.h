@@ -59,9 +59,9 @@ typedef struct ktb_oligo ktb_oligo;
 
 /* Timings of the most recent vectorise call on a handle (milliseconds, CUDA events / host clock). */
 typedef struct ktb_stats {
-    double kernel_ms;      /* device time of the compute kernels (sum over chunks) */
-    double h2d_ms;         /* host->device copy time (host-buffer entry point only) */
-    double d2h_ms;         /* device->host copy time */
+    double kernel_ms;      /* time during which a compute kernel of the call was running (chunks overlap: union, not sum) */
+    double h2d_ms;         /* time during which a host->device copy was running (host-buffer entry point only) */
+    double d2h_ms;         /* time during which a device->host copy was running */
     double wall_ms;        /* host wall clock of the whole call */
     uint64_t launches;     /* kernels launched by this library during the call */
     uint64_t h2d_bytes;

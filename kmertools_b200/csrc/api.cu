@@ -121,6 +121,7 @@ struct ktb_oligo {
     ChunkSet sets[NBUF];
     cudaStream_t aux[2] = {nullptr, nullptr};   // wave overlap in the global-atomic path
     cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ref_ev = nullptr;            // time origin of the stats of one host-buffer call
     int sm_count = 0;
     size_t smem_optin = 0;
     // options
@@ -886,6 +887,7 @@ int ktb_oligo_create(int k, int device, ktb_oligo **out) {
     }
     for (auto &a : h->aux) CUB(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
     for (auto &e : h->aux_ev) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUB(cudaEventCreate(&h->ref_ev));
     // cudaMemcpy from pageable memory may return while the DMA to the device is still in flight, and the
     // handle's non-blocking streams do not order against the default stream: make the tables visible now.
     CUB(cudaDeviceSynchronize());
@@ -911,6 +913,7 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     }
     for (auto &a : h->aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
     for (auto &e : h->aux_ev) if (e) cudaEventDestroy(e);
+    if (h->ref_ev) cudaEventDestroy(h->ref_ev);
     h->ws_totals.release();
     h->ws_counts.release();
     h->ws_list.release();
@@ -1056,19 +1059,41 @@ int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offs
     uint64_t rows_per_chunk = std::max<uint64_t>(1, (uint64_t)h->chunk_bytes / row_bytes);
     const uint64_t max_chunk_bases = 1ull << 30;
 
-    struct Pending { uint64_t i0, i1; };
-    Pending pend[NBUF];
     bool has[NBUF] = {false, false, false};
+    // h2d_ms / kernel_ms / d2h_ms are the time during which AT LEAST ONE copy (kernel) of that kind was running: the
+    // three stream sets overlap, so per-chunk durations are kept as intervals on one clock (an event recorded at the
+    // start of the call) and merged at the end — their plain sum would exceed the wall time.
+    struct Span { float a, b; };
+    std::vector<Span> spans[3];
+    CU(cudaEventRecord(h->ref_ev, h->sets[0].stream));
     auto drain = [&](int b) -> int {
         ChunkSet &s = h->sets[b];
         if (!has[b]) return KTB_OK;
         CU(cudaStreamSynchronize(s.stream));
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1])); h->stats.h2d_ms += ms;
-        CU(cudaEventElapsedTime(&ms, s.ev[4], s.ev[2])); h->stats.kernel_ms += ms;
-        CU(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3])); h->stats.d2h_ms += ms;
+        const int first[3] = {0, 4, 2}, last[3] = {1, 2, 3};
+        for (int q = 0; q < 3; ++q) {
+            Span sp{};
+            CU(cudaEventElapsedTime(&sp.a, h->ref_ev, s.ev[first[q]]));
+            CU(cudaEventElapsedTime(&sp.b, h->ref_ev, s.ev[last[q]]));
+            spans[q].push_back(sp);
+        }
         has[b] = false;
         return KTB_OK;
+    };
+    auto union_ms = [](std::vector<Span> &v) -> double {
+        std::sort(v.begin(), v.end(), [](const Span &x, const Span &y) { return x.a < y.a; });
+        double total = 0;
+        float cur_a = 0, cur_b = -1;
+        for (const Span &sp : v) {
+            if (cur_b < cur_a || sp.a > cur_b) {
+                if (cur_b >= cur_a) total += cur_b - cur_a;
+                cur_a = sp.a; cur_b = sp.b;
+            } else if (sp.b > cur_b) {
+                cur_b = sp.b;
+            }
+        }
+        if (cur_b >= cur_a) total += cur_b - cur_a;
+        return total;
     };
 
     int b = 0;
@@ -1123,13 +1148,14 @@ int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offs
         h->stats.h2d_bytes += nb + (cn + 1) * 8;
         h->stats.d2h_bytes += cn * row_bytes + (totals ? cn * 8 : 0);
         has[b] = true;
-        pend[b] = {i0, i1};
         b = (b + 1) % NBUF;
         i0 = i1;
     }
-    (void)pend;
     for (int q = 0; q < NBUF; ++q)
         if (int rc = drain(q)) return rc;
+    h->stats.h2d_ms = union_ms(spans[0]);
+    h->stats.kernel_ms = union_ms(spans[1]);
+    h->stats.d2h_ms = union_ms(spans[2]);
     h->stats.launches = total_launches;
     h->stats.wall_ms = now_ms() - t0;
     return KTB_OK;

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
         const bool more = tile_id + gridDim.x < ntiles;
         TileInfo nti = ti;
         if (more) nti = p.tiles[tile_id + gridDim.x];
-        if (tid == 0) { s_tot = 0; s_base[trash] = BK_TILE_CAP; }
+        if (tid == 0) s_tot = 0;
         if (tid <= BK_MAX_SEG) s_cnt[tid] = 0;
         __syncthreads();
         const uint64_t q0 = ti.q0, q1 = ti.q1;
@@ -171,14 +171,28 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
             rlo = (uint32_t)R64; rhi = (uint32_t)(R64 >> 32);
         }
         uint32_t cp[16];   // per window: code (20 bits, k <= 10) | position in the run << 20 (12 bits)
+        // steady state: every lane but lane 0 has 16 valid windows, so validity is ONE predicate per lane instead of a
+        // bit test per window (warp-uniform choice; invalid windows queue up in the trash segment, no branch per atomic)
+        const bool steady = __all_sync(FULL, lane == 0 || vw == 0xFFFFu);
+        const bool lane_ok = lane != 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             uint32_t code = ((j < 15) ? __funnelshift_r(cf, cf_prev, 2 * (15 - j)) : cf) & kmask;
             if constexpr (CANON) code = min(code, ((j > 0) ? __funnelshift_r(rlo, rhi, 2 * j) : rlo) & kmask);
-            // invalid windows queue up in the trash segment: no branch around the atomic
-            const uint32_t sg = (vw & (1u << (15 - j))) ? (code >> p.log2_seg) : trash;
-            const uint32_t ps = atomicAdd(&s_cnt[sg], 1u);
-            cp[j] = code | (ps << 20);
+            cp[j] = code;
+        }
+        if (steady) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t sg = lane_ok ? (cp[j] >> p.log2_seg) : trash;
+                cp[j] |= atomicAdd(&s_cnt[sg], 1u) << 20;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t sg = (vw & (1u << (15 - j))) ? (cp[j] >> p.log2_seg) : trash;
+                cp[j] |= atomicAdd(&s_cnt[sg], 1u) << 20;
+            }
         }
         if (more) v = load_chunk(nti);   // the next tile's bases are on their way while this tile is sorted
         mine = __reduce_add_sync(FULL, mine);
@@ -209,13 +223,22 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
 
         // ---- phase 3: scatter the in-segment codes to their runs (branch-free: invalid windows land in the trash
         // entries), then one bulk copy of the sorted tile into its pool slot
+        // (an invalid window reads the base of whatever segment its stale code names — harmless — and is redirected)
+        const uint32_t trash_slot = BK_TILE_CAP + lane;
+        if (steady) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const bool ok = (vw & (1u << (15 - j))) != 0u;
-            const uint32_t code = cp[j] & 0xFFFFFu;
-            const uint32_t sg = ok ? (code >> p.log2_seg) : trash;
-            const uint32_t ps = ok ? (cp[j] >> 20) : (uint32_t)lane;
-            stage[s_base[sg] + ps] = (uint16_t)(code & seg_mask);
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t code = cp[j] & 0xFFFFFu;
+                const uint32_t slot = s_base[code >> p.log2_seg] + (cp[j] >> 20);
+                stage[lane_ok ? slot : trash_slot] = (uint16_t)(code & seg_mask);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t code = cp[j] & 0xFFFFFu;
+                const uint32_t slot = s_base[code >> p.log2_seg] + (cp[j] >> 20);
+                stage[(vw & (1u << (15 - j))) ? slot : trash_slot] = (uint16_t)(code & seg_mask);
+            }
         }
         fence_async_smem();
         __syncthreads();
@@ -247,9 +270,9 @@ constexpr int CK_SEQ_CHUNK = 8;   // consecutive sequences that share one load o
 
 // One CTA per (segment of the code space, chunk of CK_SEQ_CHUNK sequences).  The columns of the segment are
 // [R, R + bins): R = rank of the segment's first code.  For every sequence of the chunk the runs of the segment (one
-// per tile of the sequence, contiguous descriptors) are dealt to HALF-WARPS — a run of ~60 codes is 15 eight-byte
+// per tile of the sequence, contiguous descriptors) are dealt to QUARTER-WARPS — a run of ~60 codes is eight 16-byte
 // loads — counted with shared-memory atomics and written out as one bulk copy (u32 / f32; f64 parts are stored
-// directly).  The first run of every half-warp is loaded BEFORE the CTA waits for the bulk copy of the previous part
+// directly).  The first run of every quarter-warp is loaded BEFORE the CTA waits for the bulk copy of the previous part
 // to leave the histogram, so that latency and the copy overlap.
 template <int OUT, bool NORM, bool CANON>
 __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams p) {
@@ -262,8 +285,8 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
     uint32_t *s_bits = csm + S;                          // CANON: bitmap of the segment's canonical codes
     uint32_t *s_pref = s_bits + wps;                     // CANON: columns before each word, relative to the segment's first
     const int tid = threadIdx.x;
-    const uint32_t hw = tid >> 4, hl = tid & 15;         // half-warp, lane in it
-    constexpr uint32_t NHW = CK_THREADS / 16;
+    const uint32_t qw = tid >> 3, ql = tid & 7;          // quarter-warp (one per run), lane in it (16 bytes = 8 codes per load)
+    constexpr uint32_t NQW = CK_THREADS / 8;
     const uint32_t ntiles = p.tile_prefix[p.n];
     const uint64_t nchunks = (p.n + CK_SEQ_CHUNK - 1) / CK_SEQ_CHUNK;
     const uint64_t nunits = nchunks * p.nseg;
@@ -301,48 +324,52 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
         const uint32_t bins = (uint32_t)(col1 - col0);   // multiple of 4 for every k this path serves (checked on the host)
         if (bins == 0) continue;                         // uniform: a segment without canonical codes
         const uint32_t *runs = p.runs + (uint64_t)seg * ntiles;
-        const uint64_t seq_end = min(p.n, (chunk + 1) * CK_SEQ_CHUNK);
-        for (uint64_t seq = chunk * CK_SEQ_CHUNK; seq < seq_end; ++seq) {
-            const uint32_t t0 = p.tile_prefix[seq], t1 = p.tile_prefix[seq + 1];
-            // ---- first run of this half-warp: descriptor and first eight bytes per lane, before the histogram is free
-            uint32_t r = t0 + hw, cnt = 0;
-            const uint2 *src = nullptr;
-            uint2 v = make_uint2(0, 0);
-            if (r < t1) {
-                const uint32_t rd = __ldg(runs + r);
-                cnt = rd & 0xFFFFu;
-                src = reinterpret_cast<const uint2 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3));
-                if (4u * hl < cnt) v = __ldg(src + hl);
-            }
+        const uint64_t seq0 = chunk * CK_SEQ_CHUNK, seq_end = min(p.n, (chunk + 1) * CK_SEQ_CHUNK);
+        // software pipeline over the sequences of the chunk: the descriptor of this quarter-warp's first run is loaded
+        // one sequence ahead, its codes at the top of the sequence's iteration — before the CTA waits for the bulk
+        // copy of the previous part to leave the histogram — so the only exposed round trip is the one to the codes
+        uint32_t t0 = p.tile_prefix[seq0], t1 = p.tile_prefix[seq0 + 1];
+        uint32_t rd = (t0 + qw < t1) ? __ldg(runs + t0 + qw) : 0u;
+        for (uint64_t seq = seq0; seq < seq_end; ++seq) {
+            uint32_t t0n = 0, t1n = 0;
+            if (seq + 1 < seq_end) { t0n = p.tile_prefix[seq + 1]; t1n = p.tile_prefix[seq + 2]; }
+            uint32_t r = t0 + qw;
+            uint32_t cnt = rd & 0xFFFFu;
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3));
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (r < t1 && 8u * ql < cnt) v = __ldg(src + ql);
             if (tid == 0 && in_flight) { bulk_wait_read(); in_flight = false; }
             __syncthreads();   // (also: the rank tables of this unit are complete)
             for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) *reinterpret_cast<uint4 *>(hist + i) = make_uint4(0, 0, 0, 0);
             __syncthreads();
-            // ---- count
+            // ---- count: one quarter-warp per run (sequences with more than NQW tiles take further rounds)
             while (r < t1) {
-                for (uint32_t q = hl; 4u * q < cnt; q += 16) {
-                    if (q != hl) v = __ldg(src + q);
-                    const uint32_t left = cnt - 4u * q;
-                    const uint32_t w[2] = {v.x, v.y};
+                for (uint32_t q = ql; 8u * q < cnt; q += 8) {
+                    if (q != ql) v = __ldg(src + q);
+                    const uint32_t left = cnt - 8u * q;
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int e4 = 0; e4 < 4; ++e4) {
-                        const uint32_t e = (e4 & 1) ? (w[e4 >> 1] >> 16) : (w[e4 >> 1] & 0xFFFFu);
+                    for (int e8 = 0; e8 < 8; ++e8) {
+                        const uint32_t e = (e8 & 1) ? (w[e8 >> 1] >> 16) : (w[e8 >> 1] & 0xFFFFu);
                         uint32_t col = e;
                         if constexpr (CANON) {
                             const uint32_t wd = (e >> 5) & (wps - 1u);   // (padding behind a run is arbitrary: stay inside the tables)
                             col = s_pref[wd] + (uint32_t)__popc(s_bits[wd] & ~(0xFFFFFFFFu << (e & 31u)));
                         }
-                        if ((uint32_t)e4 < left) atomicAdd(hist + col, 1u);
+                        if ((uint32_t)e8 < left) atomicAdd(hist + col, 1u);
                     }
                 }
-                r += NHW;
+                r += NQW;
                 if (r < t1) {
-                    const uint32_t rd = __ldg(runs + r);
-                    cnt = rd & 0xFFFFu;
-                    src = reinterpret_cast<const uint2 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3));
-                    if (4u * hl < cnt) v = __ldg(src + hl);
+                    const uint32_t rd2 = __ldg(runs + r);
+                    cnt = rd2 & 0xFFFFu;
+                    src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd2 >> 16) << 3));
+                    if (8u * ql < cnt) v = __ldg(src + ql);
                 }
             }
+            // descriptor of the next sequence's first run (its tile range arrived long ago)
+            rd = (t0n + qw < t1n) ? __ldg(runs + t0n + qw) : 0u;
+            const uint32_t t0_next = t0n, t1_next = t1n;
             __syncthreads();
             // ---- normalise and write this part of the row
             const unsigned long long total = p.totals_in[seq];
@@ -378,6 +405,7 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
                         row[i] = small ? cvt_count<OUT, NORM, true>(hist[i], dF, rinv, dD) : cvt_count<OUT, NORM, false>(hist[i], dF, rinv, dD);
                 }
             }
+            t0 = t0_next; t1 = t1_next;
         }
     }
     if (tid == 0) bulk_wait_all();

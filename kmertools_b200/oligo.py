@@ -26,14 +26,19 @@ _CODES = {np.dtype(np.uint32): OUT_U32, np.dtype(np.float32): OUT_F32, np.dtype(
 
 
 class HostBuffer:
-    """Page-locked host memory from ktb_host_alloc, viewed as a numpy array."""
+    """Page-locked host memory from ktb_host_alloc / ktb_host_alloc_near, viewed as a numpy array."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, near_device: int | None = None):
+        """near_device: bind the pages to the NUMA node of that GPU (ktb_host_alloc_near) instead of wherever the
+        calling thread happens to run — what a process that feeds one of several GPUs wants."""
         self._lib = _lib.load()
         self.dtype = np.dtype(dtype)
         self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
         nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
-        self.ptr = self._lib.ktb_host_alloc(max(nbytes, 1))
+        if near_device is None:
+            self.ptr = self._lib.ktb_host_alloc(max(nbytes, 1))
+        else:
+            self.ptr = self._lib.ktb_host_alloc_near(max(nbytes, 1), int(near_device))
         if not self.ptr:
             _lib.check(_lib.KTB_ERR_NOMEM)
         buf = (C.c_uint8 * max(nbytes, 1)).from_address(self.ptr)

@@ -293,6 +293,50 @@ int64_t ktb_oracle_format_row(const double *row, uint64_t dim, int norm, const c
     return (int64_t)w;
 }
 
+/* Timed CPU baseline of the FILE-level path (composition/src/oligo.rs:126-144): per sequence vectorise_one, then
+ * format every value ("{:.6}" / "{}") and join them into the row's String — in parallel over the sequences of the
+ * batch (rayon par_iter().map().collect()) — then the rows are written in order with one buffered writer.
+ * path == NULL skips the write.  Returns the number of text bytes produced. */
+uint64_t ktb_oracle_baseline_text(const uint8_t *bases, const uint64_t *offsets, uint64_t n, int k, int canonical,
+                                  int norm, const char *delim, const char *path, int threads, int *threads_used) {
+    const uint64_t ncodes = 1ULL << (2 * k);
+    uint64_t *pos_map = (uint64_t *)malloc(ncodes * sizeof(uint64_t));
+    const uint64_t cnt = ktb_oracle_kmer_pos_maps(k, pos_map, NULL);
+    const uint64_t dim = canonical ? cnt : ncodes;
+    char **rows = (char **)malloc(n * sizeof(char *));
+    uint64_t *lens = (uint64_t *)malloc(n * sizeof(uint64_t));
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#else
+    threads = 1;
+#endif
+    if (threads_used) *threads_used = threads;
+    const uint64_t cap = dim * 24 + 64;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        double *row = (double *)malloc(dim * sizeof(double));
+        ktb_oracle_vectorise_one(bases + offsets[i], offsets[i + 1] - offsets[i], k, pos_map, canonical, norm ? 1 : 0,
+                                 row, dim);
+        char *txt = (char *)malloc(cap);
+        const int64_t w = ktb_oracle_format_row(row, dim, norm, delim, txt, cap);
+        rows[i] = txt;
+        lens[i] = w > 0 ? (uint64_t)w : 0;
+        free(row);
+    }
+    uint64_t total = 0;
+    FILE *fo = path ? fopen(path, "wb") : NULL;
+    for (uint64_t i = 0; i < n; i++) {
+        if (fo) fwrite(rows[i], 1, lens[i], fo);
+        total += lens[i];
+        free(rows[i]);
+    }
+    if (fo) fclose(fo);
+    free(rows);
+    free(lens);
+    free(pos_map);
+    return total;
+}
+
 /* Checker for the GPU's f32 normalisation (kmertools_b200/csrc/kernels.cuh quot_f32): the same
  * three-operation sequence in C — q0 = c*RN(1/d); rem = fma(-q0,d,c); q = fma(rem,RN(1/d),q0) — must
  * equal (float)((double)c/(double)d), the reference's f64 quotient rounded once, for every

@@ -61,6 +61,9 @@ def lib() -> C.CDLL:
                                                 C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.ktb_oracle_max_threads.restype = C.c_int
         L.ktb_oracle_header.restype = C.c_int
+        L.ktb_oracle_baseline_text.restype = C.c_uint64
+        L.ktb_oracle_baseline_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                               C.c_char_p, C.c_int, C.POINTER(C.c_int)]
         L.ktb_oracle_header.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_uint64]
         L.ktb_oracle_format_row.restype = C.c_int64
         L.ktb_oracle_format_row.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_char_p, C.c_char_p,
@@ -167,6 +170,19 @@ def baseline_batch(bases: np.ndarray, offsets: np.ndarray, k: int, canonical: bo
     cs = lib().ktb_oracle_baseline_batch(bases.ctypes.data, offsets.ctypes.data, n, k, int(canonical),
                                          norm_mode, threads, C.byref(used))
     return float(cs), int(used.value)
+
+
+def baseline_text(bases: np.ndarray, offsets: np.ndarray, k: int, canonical: bool = True, norm: bool = True,
+                  delim: str = " ", path: str | None = None, threads: int = 0) -> tuple[int, int]:
+    """CPU baseline of the file-level path (vectorise + format every value + ordered write), composition/src/oligo.rs:
+    126-144.  Returns (text bytes, threads used)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    used = C.c_int(0)
+    nbytes = lib().ktb_oracle_baseline_text(bases.ctypes.data if bases.size else np.zeros(1, np.uint8).ctypes.data,
+                                            offsets.ctypes.data, len(offsets) - 1, k, int(canonical), int(norm),
+                                            delim.encode(), os.fsencode(path) if path else None, threads, C.byref(used))
+    return int(nbytes), int(used.value)
 
 
 def check_quot_f32(dlo: int, dhi: int, cstep: int = 1) -> int:

@@ -76,7 +76,7 @@ def test_config5ii_all_sequences_bit_exact():
     from kmertools_b200 import OligoComputer
     spec = bench.WORKLOADS["reads100k_k10"]
     dev = torch.device("cuda", 0)
-    bases, offsets = bench.make_workload(spec, 1.0, dev)
+    bases, offsets = bench.make_workload_torch(spec, 1.0, dev)
     n, k = offsets.numel() - 1, spec["k"]
     assert n == 2000
     oc = OligoComputer(k)

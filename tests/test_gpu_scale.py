@@ -32,7 +32,7 @@ def test_baseline_shapes_by_properties(workload, scale):
     from kmertools_b200 import OligoComputer
     spec = bench.WORKLOADS[workload]
     dev = torch.device("cuda", 0)
-    bases, offsets = bench.make_workload(spec, scale, dev)
+    bases, offsets = bench.make_workload_torch(spec, scale, dev)
     n, L, k = offsets.numel() - 1, int(spec["length"]), spec["k"]
     oc = OligoComputer(k)
     counts = oc.vectorise_tensors(bases, offsets, norm_mode=0, dtype=torch.int32)
@@ -76,7 +76,7 @@ def test_contigs_shape_by_properties():
     from kmertools_b200 import OligoComputer
     spec = bench.WORKLOADS["contigs_k4"]
     dev = torch.device("cuda", 0)
-    bases, offsets = bench.make_workload(spec, 0.02, dev)   # 400 contigs, ~30 Mbases
+    bases, offsets = bench.make_workload_torch(spec, 0.02, dev)   # 400 contigs, ~30 Mbases
     n = offsets.numel() - 1
     oc = OligoComputer(4)
     totals = torch.zeros(n, dtype=torch.int64, device=dev)

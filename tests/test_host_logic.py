@@ -50,3 +50,29 @@ def test_shard_bounds_matches_the_python_sharder():
                 if len(lengths) and lengths.sum():
                     per = [int(offs[b[r + 1]]) - int(offs[b[r]]) for r in range(parts)]
                     assert max(per) - lengths.sum() / parts <= lengths.max()
+
+
+def test_bench_generator_is_backend_independent_and_prefix_stable():
+    """bench.py's workloads are hashes of (seed, position / read index): numpy and torch produce the same bytes, and
+    the first m sequences do not depend on how many follow — so the CPU arms time a prefix of the GPU arm's data."""
+    import torch
+    import bench
+    for name, scale in (("reads150_k5", 0.0005), ("reads10k_k7", 0.0003), ("contigs_k4", 0.004), ("reads100k_k10", 0.02)):
+        spec = bench.WORKLOADS[name]
+        bn, on = bench.make_workload(spec, scale, bench._NP())
+        bt, ot = bench.make_workload_torch(spec, scale, torch.device("cpu"))
+        assert np.array_equal(bn, bt.numpy()) and np.array_equal(on, ot.numpy()), name
+        m = 7
+        bp, op = bench.make_workload(spec, scale, bench._NP(), n_limit=m)
+        assert np.array_equal(op, on[: m + 1]) and np.array_equal(bp, bn[: int(on[m])]), name
+        cfg = bench.config_of(name, spec, scale)
+        assert cfg["sequences_per_gpu"] == len(on) - 1 and cfg["bases_per_gpu"] == int(on[-1])
+        # the alphabet the config promises
+        letters = set(bytes(bn.tobytes()))
+        assert letters >= set(b"ACGT") and ord("N") in letters or name == "reads100k_k10"
+    spec = bench.WORKLOADS["contigs_k4"]
+    b, o = bench.make_workload(spec, 0.01, bench._NP())
+    L = np.diff(o)
+    assert L.min() >= 1000 and L.max() <= 500_000
+    frac_n = float((b == ord("N")).mean())
+    assert 0.0 < frac_n < 0.2 and (np.isin(b, list(b"acgt"))).mean() > 0.01 and np.isin(b, list(b"RYKMSW")).any()
