@@ -230,6 +230,10 @@ void ktb_free(void *p);
 int ktb_debug_fastx_batches(const char *path, int sniff, uint64_t max_records, uint64_t batch_bytes, uint8_t **bases,
                             uint64_t **offsets, uint64_t *n);
 
+/* The output writer of the file-level drivers on its own (csrc/span_writer.h): `data` goes to `path` in blocks of `block`
+ * bytes, asynchronously, by `threads` threads through a shared mapping (mapped != 0) or by one thread with write(). */
+int ktb_debug_span_write(const char *path, const uint8_t *data, uint64_t len, uint64_t block, int threads, int mapped);
+
 /* Host build of the GPU text formatter: 8 characters "d.dddddd" = Rust's format!("{:.6}", q), q in [0,1]. */
 int ktb_debug_format6(double q, char *out8);
 

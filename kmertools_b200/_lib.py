@@ -74,6 +74,7 @@ SYMBOLS = {
     "ktb_release_cached_buffers": (None, []),
     "ktb_fastx_load": (_I, [C.c_char_p, _I, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_U64)]),
     "ktb_debug_fastx_batches": (_I, [C.c_char_p, _I, _U64, _U64, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_U64)]),
+    "ktb_debug_span_write": (_I, [C.c_char_p, _VP, _U64, _U64, _I, _I]),
     "ktb_free": (None, [_VP]),
     "ktb_debug_format6": (_I, [C.c_double, C.c_char_p]),
     "ktb_debug_nt4_table": (_I, [_VP, _VP]),

@@ -278,6 +278,7 @@ template <int OUT, bool NORM, bool CANON>
 __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams p) {
     extern __shared__ __align__(128) uint32_t csm[];
     __shared__ unsigned long long s_unit;
+    __shared__ uint32_t s_tp[CK_SEQ_CHUNK + 1];   // tile prefix of the chunk's sequences
     using T = typename OutT<OUT>::type;
     const uint32_t S = 1u << p.log2_seg;                 // codes per segment
     const uint32_t wps = S / 32;                         // bitmap words per segment
@@ -325,21 +326,27 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
         if (bins == 0) continue;                         // uniform: a segment without canonical codes
         const uint32_t *runs = p.runs + (uint64_t)seg * ntiles;
         const uint64_t seq0 = chunk * CK_SEQ_CHUNK, seq_end = min(p.n, (chunk + 1) * CK_SEQ_CHUNK);
-        // software pipeline over the sequences of the chunk: the descriptor of this quarter-warp's first run is loaded
-        // one sequence ahead, its codes at the top of the sequence's iteration — before the CTA waits for the bulk
-        // copy of the previous part to leave the histogram — so the only exposed round trip is the one to the codes
+        // software pipeline over the sequences of the chunk: while sequence i is counted, the descriptor of this
+        // quarter-warp's first run of sequence i+1 is already loaded and its codes are requested right after the atomics
+        // of i — one write-out, one wait for the previous bulk copy and one zeroing ahead of their use
+        if (tid <= CK_SEQ_CHUNK) s_tp[tid] = p.tile_prefix[min(p.n, seq0 + tid)];
         uint32_t t0 = p.tile_prefix[seq0], t1 = p.tile_prefix[seq0 + 1];
         uint32_t rd = (t0 + qw < t1) ? __ldg(runs + t0 + qw) : 0u;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (t0 + qw < t1 && 8u * ql < (rd & 0xFFFFu))
+            v = __ldg(reinterpret_cast<const uint4 *>(p.pool + (uint64_t)(t0 + qw) * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3)) + ql);
         for (uint64_t seq = seq0; seq < seq_end; ++seq) {
-            uint32_t t0n = 0, t1n = 0;
-            if (seq + 1 < seq_end) { t0n = p.tile_prefix[seq + 1]; t1n = p.tile_prefix[seq + 2]; }
             uint32_t r = t0 + qw;
             uint32_t cnt = rd & 0xFFFFu;
             const uint4 *src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3));
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (r < t1 && 8u * ql < cnt) v = __ldg(src + ql);
             if (tid == 0 && in_flight) { bulk_wait_read(); in_flight = false; }
-            __syncthreads();   // (also: the rank tables of this unit are complete)
+            __syncthreads();   // (also: the rank tables and s_tp of this unit are complete)
+            // descriptor of the next sequence's first run
+            uint32_t t0n = 0, t1n = 0, rdn = 0;
+            if (seq + 1 < seq_end) {
+                t0n = s_tp[seq + 1 - seq0]; t1n = s_tp[seq + 2 - seq0];
+                if (t0n + qw < t1n) rdn = __ldg(runs + t0n + qw);
+            }
             for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) *reinterpret_cast<uint4 *>(hist + i) = make_uint4(0, 0, 0, 0);
             __syncthreads();
             // ---- count: one quarter-warp per run (sequences with more than NQW tiles take further rounds)
@@ -367,8 +374,11 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
                     if (8u * ql < cnt) v = __ldg(src + ql);
                 }
             }
-            // descriptor of the next sequence's first run (its tile range arrived long ago)
-            rd = (t0n + qw < t1n) ? __ldg(runs + t0n + qw) : 0u;
+            // codes of the next sequence's first run: in flight during this sequence's write-out
+            v = make_uint4(0, 0, 0, 0);
+            if (t0n + qw < t1n && 8u * ql < (rdn & 0xFFFFu))
+                v = __ldg(reinterpret_cast<const uint4 *>(p.pool + (uint64_t)(t0n + qw) * BK_TILE_CAP + ((uint64_t)(rdn >> 16) << 3)) + ql);
+            rd = rdn;
             const uint32_t t0_next = t0n, t1_next = t1n;
             __syncthreads();
             // ---- normalise and write this part of the row

@@ -271,6 +271,24 @@ int ktb_fastx_load(const char *path, int sniff, uint8_t **bases, uint64_t **offs
     return KTB_OK;
 }
 
+int ktb_debug_span_write(const char *path, const uint8_t *data, uint64_t len, uint64_t block, int threads, int mapped) {
+    if (!path || (len && !data) || !block) return ktb_internal_fail(KTB_ERR_ARG, "bad argument");
+    setenv("KTB_WRITER", mapped ? "map" : "seq", 1);
+    ktb::SpanWriter wr;
+    std::string err;
+    const bool ok = wr.open(path, threads, &err);
+    unsetenv("KTB_WRITER");
+    if (!ok) return ktb_internal_fail(KTB_ERR_IO, err.c_str());
+    std::vector<ktb::SpanWriter::Ticket> tickets((size_t)((len + block - 1) / block) + 1);
+    size_t t = 0;
+    for (uint64_t a = 0; a < len; a += block, ++t) wr.submit(data + a, (size_t)std::min(block, len - a), &tickets[t]);
+    bool good = true;
+    for (size_t i = 0; i < t; ++i) good &= wr.wait(&tickets[i]);
+    if (wr.bytes() != len) good = false;
+    if (!wr.close()) good = false;
+    return good ? KTB_OK : ktb_internal_fail(KTB_ERR_IO, "write to the output file failed");
+}
+
 int ktb_debug_fastx_batches(const char *path, int sniff, uint64_t max_records, uint64_t batch_bytes, uint8_t **bases,
                             uint64_t **offsets, uint64_t *n) {
     if (!path || !bases || !offsets || !n || !max_records || !batch_bytes) return ktb_internal_fail(KTB_ERR_ARG, "bad argument");

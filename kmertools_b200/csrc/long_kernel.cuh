@@ -226,19 +226,20 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
             if (s1 - s0 >= k) {
                 const uint64_t cbase = s0 >> 4;
                 const uint32_t nch = (uint32_t)(((s1 - 1) >> 4) - cbase) + 1u;
-                const uint32_t nsteps = (nch + 31) >> 5;
-                // contiguous runs of whole 32-chunk steps per warp
-                const uint32_t w0 = ((warp * nsteps) / NW) << 5;
-                const uint32_t w1 = min(nch, (((warp + 1) * nsteps) / NW) << 5);
+                // Contiguous runs of whole 32-chunk steps per warp.  A warp that starts inside the sequence loads, in lane 0 of
+                // its first step, the LAST chunk of the previous warp as look-back (that lane emits nothing), so no warp has
+                // to load and decode a priming chunk on its own: such a warp covers 32 * steps - 1 new chunks, and the step
+                // count carries NW - 1 chunks of slack.  Sequences of fewer steps than warps use the first warps only.
+                const uint32_t nsteps = (nch + (NW - 1) + 31) >> 5;
+                const uint32_t q0 = nsteps >= NW ? (warp * nsteps) / NW : min(warp, nsteps);
+                const uint32_t q1 = nsteps >= NW ? ((warp + 1) * nsteps) / NW : min(warp + 1, nsteps);
+                const bool lookback = q0 > 0;                                   // lane 0 of the first step re-reads chunk w0
+                const uint32_t w0 = lookback ? (q0 << 5) - warp : 0u;
+                const uint32_t w1 = min(nch, (q1 << 5) - warp);
                 const uint32_t head_mask = 0xFFFFu >> (uint32_t)(s0 & 15);
                 const uint32_t tail_mask = ~(0xFFFFu >> ((uint32_t)((s1 - 1) & 15) + 1u)) & 0xFFFFu;
-                if (w0 < w1) {
+                if (q0 < q1 && w0 < w1) {
                     uint32_t carry_cf = 0, carry_vm = 0;
-                    if (w0 > 0) {   // prime the look-back with the chunk before this warp's range
-                        const uint4 v = load16_guarded(p.bases, (cbase + w0 - 1) << 4, p.total_bases);
-                        decode16(v, carry_cf, carry_vm);
-                        if (w0 == 1) carry_vm &= head_mask;
-                    }
                     const uint4 *seq_chunks = reinterpret_cast<const uint4 *>(p.bases) + cbase;
                     const bool near_end = ((cbase + nch) << 4) > p.total_bases;
                     auto fetch = [&](uint32_t c) -> uint4 {
@@ -264,7 +265,9 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
                         if (lane == 0) { cf_prev = carry_cf; vm_prev = carry_vm; }
                         carry_cf = __shfl_sync(FULL, cf, 31);
                         carry_vm = __shfl_sync(FULL, vm, 31);
-                        const uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
+                        uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
+                        const bool silent = lookback && c0 == w0 && lane == 0;   // the look-back lane of this warp's first step
+                        if (silent) vw = 0;
                         mine += __popc(vw);
                         uint32_t off[16];   // histogram byte offsets; off[e] = window ending at base e
                         if constexpr (MODE == MODE_K7) {
@@ -282,6 +285,10 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
                         if (__all_sync(FULL, vw == 0xFFFFu)) {
 #pragma unroll
                             for (int e = 0; e < 16; ++e) atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), 1u);
+                        } else if (__all_sync(FULL, silent || vw == 0xFFFFu)) {   // full step behind a look-back lane
+                            const uint32_t inc = silent ? 0u : 1u;
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), inc);
                         } else {
 #pragma unroll
                             for (int e = 0; e < 16; ++e)   // branch-free: an invalid window adds 0

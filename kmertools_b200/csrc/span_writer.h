@@ -11,6 +11,7 @@
 #pragma once
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -46,7 +47,10 @@ public:
             return false;
         }
         struct stat sb;
-        mapped_ = fstat(fd_, &sb) == 0 && S_ISREG(sb.st_mode) && (fcntl(fd_, F_GETFL) & O_ACCMODE) == O_RDWR;
+        // KTB_WRITER=map | seq overrides the choice (measurements: profiles/r2_cli_writer.txt)
+        const char *want = getenv("KTB_WRITER");
+        const bool try_map = want ? !strcmp(want, "map") : kMapByDefault;
+        mapped_ = try_map && fstat(fd_, &sb) == 0 && S_ISREG(sb.st_mode) && (fcntl(fd_, F_GETFL) & O_ACCMODE) == O_RDWR;
         if (mapped_) {   // some file systems refuse shared mappings: probe once
             if (ftruncate(fd_, 4096) != 0) mapped_ = false;
             else {
@@ -110,6 +114,7 @@ public:
 
 private:
     static constexpr size_t kSpan = 8u << 20;
+    static constexpr bool kMapByDefault = false;
     struct Job {
         const char *src;
         uint64_t off;

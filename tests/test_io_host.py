@@ -174,3 +174,23 @@ def test_gzip_only_the_first_member_is_read(tmp_path):
         kio.read_fastx(_write(tmp_path, "p.fa.gz", gzip.compress(big)[:-40]))
     with pytest.raises(KtbError):   # ".gz" that is not gzip
         kio.read_fastx(_write(tmp_path, "q.fa.gz", b">r1\nACGT\n"))
+
+
+@pytest.mark.parametrize("mapped", [0, 1])
+def test_span_writer_orders_blocks_and_handles_odd_sizes(tmp_path, mapped):
+    """The drivers' output writer (csrc/span_writer.h): blocks submitted in order end up in order, whatever the block
+    size, span boundaries (8 MB) and thread count; the file has exactly the submitted length."""
+    import ctypes as C
+    from kmertools_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(mapped)
+    for nbytes, block, threads in ((0, 4096, 4), (1, 1, 1), (12345, 1000, 3), (9_000_001, 1_234_567, 8), (20_000_003, 17_000_000, 4)):
+        data = rng.integers(0, 256, size=nbytes, dtype=np.uint8)
+        p = tmp_path / f"w{mapped}_{nbytes}.bin"
+        _lib.check(L.ktb_debug_span_write(str(p).encode(), data.ctypes.data if nbytes else None, nbytes, block, threads, mapped))
+        assert p.read_bytes() == data.tobytes()
+    # not a regular file: written sequentially whatever was asked for
+    _lib.check(L.ktb_debug_span_write(b"/dev/null", data.ctypes.data, len(data), 4096, 4, mapped))
+    from kmertools_b200 import KtbError
+    with pytest.raises(KtbError, match="Unable to write"):
+        _lib.check(L.ktb_debug_span_write(str(tmp_path / "no" / "dir" / "x").encode(), data.ctypes.data, 10, 4, 1, mapped))
