@@ -322,7 +322,9 @@ int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
         const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
         // 4 warps per CTA for reads of a few steps per warp (10 kbp = 20 steps: 5 per warp, balanced, half the per-warp
         // set-up of 8 warps); 8 warps for long contigs
-        int nw = h->long_warps > 0 ? h->long_warps : (mean_len <= 32768 ? 4 : 8);
+        // measured (profiles/r2_sweeps.txt): k = 7 rows want as many warps as fit (10 per CTA, three CTAs per SM of
+        // 64 KB each; 10 divides the 20 steps of a 10 kbp read); the small histograms of k <= 5 run best with 4 warps
+        int nw = h->long_warps > 0 ? h->long_warps : (mode == MODE_K7 ? (mean_len <= 32768 ? 10 : 8) : (mean_len <= 32768 ? 4 : 8));
         if (nw == 10 && mode != MODE_K7) nw = 8;
         void (*kern)(const LongParams) = nullptr;
         if (mode == MODE_K7) {

@@ -279,10 +279,11 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
     extern __shared__ __align__(128) uint32_t csm[];
     __shared__ unsigned long long s_unit;
     __shared__ uint32_t s_tp[CK_SEQ_CHUNK + 1];   // tile prefix of the chunk's sequences
+    __shared__ uint32_t s_rd[CK_THREADS];         // descriptor of every quarter-warp's first run, per sequence of the chunk
+    static_assert(CK_THREADS == CK_SEQ_CHUNK * (CK_THREADS / 8), "one descriptor slot per (sequence, quarter-warp)");
     using T = typename OutT<OUT>::type;
     const uint32_t S = 1u << p.log2_seg;                 // codes per segment
     const uint32_t wps = S / 32;                         // bitmap words per segment
-    uint32_t *hist = csm;                                // up to S bins
     uint32_t *s_bits = csm + S;                          // CANON: bitmap of the segment's canonical codes
     uint32_t *s_pref = s_bits + wps;                     // CANON: columns before each word, relative to the segment's first
     const int tid = threadIdx.x;
@@ -295,7 +296,6 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
     // dynamically; the counter is read one unit ahead to keep its round trip off the critical path
     unsigned long long next_unit = 0;
     if (tid == 0) next_unit = atomicAdd(p.counter, 1ULL);
-    bool in_flight = false;   // (tid 0) a bulk copy out of `hist` may still be reading it
     for (;;) {
         __syncthreads();      // everyone is done with s_unit and the tables of the previous unit
         if (tid == 0) {
@@ -326,27 +326,44 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
         if (bins == 0) continue;                         // uniform: a segment without canonical codes
         const uint32_t *runs = p.runs + (uint64_t)seg * ntiles;
         const uint64_t seq0 = chunk * CK_SEQ_CHUNK, seq_end = min(p.n, (chunk + 1) * CK_SEQ_CHUNK);
-        // software pipeline over the sequences of the chunk: while sequence i is counted, the descriptor of this
-        // quarter-warp's first run of sequence i+1 is already loaded and its codes are requested right after the atomics
-        // of i — one write-out, one wait for the previous bulk copy and one zeroing ahead of their use
-        if (tid <= CK_SEQ_CHUNK) s_tp[tid] = p.tile_prefix[min(p.n, seq0 + tid)];
-        uint32_t t0 = p.tile_prefix[seq0], t1 = p.tile_prefix[seq0 + 1];
-        uint32_t rd = (t0 + qw < t1) ? __ldg(runs + t0 + qw) : 0u;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (t0 + qw < t1 && 8u * ql < (rd & 0xFFFFu))
-            v = __ldg(reinterpret_cast<const uint4 *>(p.pool + (uint64_t)(t0 + qw) * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3)) + ql);
+        // software pipeline over the sequences of the chunk: the descriptors of every quarter-warp's first run are
+        // fetched for all sequences of the chunk at once, and the codes of sequence i+1 are requested at the top of
+        // iteration i — a whole iteration (count, write-out, wait for the previous bulk copy, zeroing) ahead of their use
+        // segments with at most S / 2 columns (the upper half of the code space: fewer and fewer codes are canonical)
+        // alternate between the two halves of the histogram memory, so the CTA never waits for its own last bulk copy
+        const bool two = bins * 2u <= S;
+        if (tid == 0) bulk_wait_read();   // buffers change roles between units
+        {
+            const uint32_t j = tid >> 5, q = tid & 31;   // CK_THREADS = CK_SEQ_CHUNK * NQW
+            const uint32_t a0 = p.tile_prefix[min(p.n, seq0 + j)], a1 = p.tile_prefix[min(p.n, seq0 + j + 1)];
+            s_rd[tid] = (a0 + q < a1) ? __ldg(runs + a0 + q) : 0u;
+            if (q == 0) s_tp[j] = a0;
+            if (tid == CK_THREADS - 1) s_tp[CK_SEQ_CHUNK] = a1;
+        }
+        __syncthreads();
+        auto first_codes = [&](uint32_t i) -> uint4 {   // this lane's 16 bytes of the first run of the chunk's i-th sequence
+            const uint32_t rdi = s_rd[i * NQW + qw];
+            if (8u * ql >= (rdi & 0xFFFFu)) return make_uint4(0, 0, 0, 0);
+            return __ldg(reinterpret_cast<const uint4 *>(p.pool + (uint64_t)(s_tp[i] + qw) * BK_TILE_CAP + ((uint64_t)(rdi >> 16) << 3)) + ql);
+        };
+        uint4 v = first_codes(0);
         for (uint64_t seq = seq0; seq < seq_end; ++seq) {
+            const uint32_t si = (uint32_t)(seq - seq0);
+            const uint32_t t0 = s_tp[si], t1 = s_tp[si + 1];
+            const uint32_t rd = s_rd[si * NQW + qw];
+            uint4 vnext = make_uint4(0, 0, 0, 0);
+            if (seq + 1 < seq_end) vnext = first_codes(si + 1);
             uint32_t r = t0 + qw;
             uint32_t cnt = rd & 0xFFFFu;
             const uint4 *src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3));
-            if (tid == 0 && in_flight) { bulk_wait_read(); in_flight = false; }
-            __syncthreads();   // (also: the rank tables and s_tp of this unit are complete)
-            // descriptor of the next sequence's first run
-            uint32_t t0n = 0, t1n = 0, rdn = 0;
-            if (seq + 1 < seq_end) {
-                t0n = s_tp[seq + 1 - seq0]; t1n = s_tp[seq + 2 - seq0];
-                if (t0n + qw < t1n) rdn = __ldg(runs + t0n + qw);
+            // the bulk copy that last used this buffer must have read it: the previous part (one buffer) or the one
+            // before it (two buffers, see `two`)
+            uint32_t *hist = csm + (two ? (si & 1u) * (S / 2) : 0u);
+            if (tid == 0) {
+                if (two) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else bulk_wait_read();
             }
+            __syncthreads();
             for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) *reinterpret_cast<uint4 *>(hist + i) = make_uint4(0, 0, 0, 0);
             __syncthreads();
             // ---- count: one quarter-warp per run (sequences with more than NQW tiles take further rounds)
@@ -374,12 +391,7 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
                     if (8u * ql < cnt) v = __ldg(src + ql);
                 }
             }
-            // codes of the next sequence's first run: in flight during this sequence's write-out
-            v = make_uint4(0, 0, 0, 0);
-            if (t0n + qw < t1n && 8u * ql < (rdn & 0xFFFFu))
-                v = __ldg(reinterpret_cast<const uint4 *>(p.pool + (uint64_t)(t0n + qw) * BK_TILE_CAP + ((uint64_t)(rdn >> 16) << 3)) + ql);
-            rd = rdn;
-            const uint32_t t0_next = t0n, t1_next = t1n;
+            v = vnext;
             __syncthreads();
             // ---- normalise and write this part of the row
             const unsigned long long total = p.totals_in[seq];
@@ -409,13 +421,12 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
                     }
                     fence_async_smem();
                     __syncthreads();
-                    if (tid == 0) { bulk_store(row, hist, bins * 4u); in_flight = true; }
+                    if (tid == 0) bulk_store(row, hist, bins * 4u);
                 } else {   // a part that does not start on a 16-byte boundary: plain coalesced stores
                     for (uint32_t i = tid; i < bins; i += CK_THREADS)
                         row[i] = small ? cvt_count<OUT, NORM, true>(hist[i], dF, rinv, dD) : cvt_count<OUT, NORM, false>(hist[i], dF, rinv, dD);
                 }
             }
-            t0 = t0_next; t1 = t1_next;
         }
     }
     if (tid == 0) bulk_wait_all();

@@ -122,14 +122,8 @@ __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hby
         constexpr uint32_t niter = K7_BINS >> 7;   // 128 (bin, rank) pairs per warp iteration
         const float nK = -8388608.0f * rinv;
         (void)nK;
-        // the schedule comes from L2: two iterations in flight
-        uint4 e_a = __ldg(sched4 + warp * 32);
-        uint4 e_b = __ldg(sched4 + (warp + NW) * 32);
-#pragma unroll 2
-        for (uint32_t w = warp; w < niter; w += NW) {
-            const uint4 e4 = e_a;
-            e_a = e_b;
-            if (w + 2 * NW < niter) e_b = __ldg(sched4 + (w + 2 * NW) * 32);
+        // one warp iteration = 128 (bin, rank) pairs = four conflict-free groups
+        auto move4 = [&](const uint4 e4) {
             const uint32_t ee[4] = {e4.x, e4.y, e4.z, e4.w};
             uint32_t bits[4];
 #pragma unroll
@@ -158,6 +152,20 @@ __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hby
                     val = NORM ? (float)((double)cnt / dD) : (float)cnt;
                 }
                 *reinterpret_cast<T *>(sbytes + (ee[q] >> 16)) = val;
+            }
+        };
+        // the schedule comes from L2: two iterations in flight, registers A / B alternate (no copies between them)
+        static_assert(niter % (2 * NW) == 0 || NW == 10, "iterations per warp");
+        uint4 A = __ldg(sched4 + warp * 32);
+        uint4 B = (warp + NW < niter) ? __ldg(sched4 + (warp + NW) * 32) : make_uint4(0, 0, 0, 0);
+        for (uint32_t w = warp; w < niter; w += 2 * NW) {
+            const uint4 a = A;
+            if (w + 2 * NW < niter) A = __ldg(sched4 + (w + 2 * NW) * 32);
+            move4(a);
+            if (w + NW < niter) {
+                const uint4 b = B;
+                if (w + 3 * NW < niter) B = __ldg(sched4 + (w + 3 * NW) * 32);
+                move4(b);
             }
         }
     } else {

@@ -1,13 +1,17 @@
 // span_writer.h — ordered, asynchronous output of the file-level drivers.
 //
 // The reference pre-sizes its output and lets N workers write disjoint rows through a shared mapping
-// (composition/src/oligo.rs:167-229, ktio/src/mmap.rs:6-47: memmap2 + write_at).  Same idea here, batch-wise: the
-// caller hands over a finished block of text; its file offset is fixed at that moment (submission order = file
-// order), the file is extended, and a small pool of threads copies 8 MB spans of the block into a shared mapping
-// of their part of the file.  Mapped copies do not take the inode write lock that serialises write()/pwrite() on
-// one file, so the spans really proceed in parallel (page allocation included), and the caller goes on parsing the
-// next batch while they do.  Outputs that cannot be mapped (pipes, character devices, /dev/stdout) are written with
-// write() by ONE pool thread in submission order.
+// (composition/src/oligo.rs:167-229, ktio/src/mmap.rs:6-47: memmap2 + write_at).  Here the caller hands over a finished
+// block of text; its file offset is fixed at that moment (submission order = file order) and the block is written
+// asynchronously while the caller parses the next batch:
+//   * on memory file systems (tmpfs, ramfs) the file is extended and `threads` threads copy 8 MB spans of the block
+//     into a shared mapping of their part of the file — mapped copies do not take the inode lock that serialises
+//     write() / pwrite() on one file;
+//   * on disk file systems ONE thread appends with write(): measured on the GPU boxes (ext4, profiles/r2_cli_writer.txt)
+//     a single buffered writer sustains 5.4 GB/s, eight mapping threads 2.9 GB/s (a write fault per 4 KB page goes
+//     through block allocation and the journal), and round 1 measured parallel pwrite() slower than one writer;
+//   * pipes, character devices and /dev/stdout cannot be mapped and take the sequential path as well.
+// KTB_WRITER=map | seq overrides the choice.
 #pragma once
 #include <condition_variable>
 #include <cstdint>
@@ -22,6 +26,7 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/vfs.h>
 #include <unistd.h>
 
 namespace ktb {
@@ -49,7 +54,10 @@ public:
         struct stat sb;
         // KTB_WRITER=map | seq overrides the choice (measurements: profiles/r2_cli_writer.txt)
         const char *want = getenv("KTB_WRITER");
-        const bool try_map = want ? !strcmp(want, "map") : kMapByDefault;
+        struct statfs sfs;
+        const bool memory_fs = fstatfs(fd_, &sfs) == 0 && ((unsigned long)sfs.f_type == 0x01021994ul /* tmpfs */ ||
+                                                            (unsigned long)sfs.f_type == 0x858458f6ul /* ramfs */);
+        const bool try_map = want ? !strcmp(want, "map") : memory_fs;
         mapped_ = try_map && fstat(fd_, &sb) == 0 && S_ISREG(sb.st_mode) && (fcntl(fd_, F_GETFL) & O_ACCMODE) == O_RDWR;
         if (mapped_) {   // some file systems refuse shared mappings: probe once
             if (ftruncate(fd_, 4096) != 0) mapped_ = false;
@@ -114,7 +122,6 @@ public:
 
 private:
     static constexpr size_t kSpan = 8u << 20;
-    static constexpr bool kMapByDefault = false;
     struct Job {
         const char *src;
         uint64_t off;
