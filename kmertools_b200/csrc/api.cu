@@ -117,7 +117,8 @@ struct ktb_oligo {
     uint32_t *d_short_tab_raw = nullptr;
     unsigned long long *d_counters = nullptr;  // [4]
     DevBuf ws_totals, ws_counts, ws_list, ws_list2;
-    DevBuf ws_tiles, ws_pool, ws_runs;     // bucket path: tile prefix, sorted index pool, run descriptors
+    DevBuf ws_tiles, ws_pool, ws_runs, ws_wavectr;   // bucket path: tile prefix + records, sorted code pool, run descriptors, work counters
+    std::vector<cudaEvent_t> wave_ev;      // bucket path: bucket_kernel(w) done
     ChunkSet sets[NBUF];
     cudaStream_t aux[2] = {nullptr, nullptr};   // wave overlap in the global-atomic path
     cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
@@ -136,6 +137,7 @@ struct ktb_oligo {
     int fwd_fold = 1;     // long_kernel MODE_FWD (3 <= k <= 6 canonical, long sequences, u32 / f32 rows)
     int64_t fwd_min_len = 1024;   // mean sequence length from which MODE_FWD replaces seq_kernel mode 1
     int bucket = 1;       // rows larger than shared memory: bucket_kernel + count_kernel instead of global atomics
+    int bucket_waves = 8;       // waves of that path (bucket_kernel of wave w+1 overlaps count_kernel of wave w)
     int bucket_log2_seg = 14;   // columns per segment of that path (2^14 u32 bins = 64 KB of shared memory)
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
     int global_steps_per_warp = 1;
@@ -485,7 +487,6 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         if (int rc = h->ws_runs.ensure(ntiles_bound * nseg * 4)) return rc;
         uint32_t *tile_prefix = (uint32_t *)h->ws_tiles.p;
         TileInfo *tiles = (TileInfo *)((uint8_t *)h->ws_tiles.p + (((n + 1) * 4 + 63) & ~(uint64_t)63));
-        CU(cudaMemsetAsync(h->d_counters + 8, 0, 3 * sizeof(unsigned long long), st));
         tile_prefix_kernel<<<1, 1024, 0, st>>>(d_offsets, n, (uint32_t)h->k, tile_prefix);
         tile_info_kernel<<<(unsigned)std::min<uint64_t>((ntiles_bound + 255) / 256, (uint64_t)h->sm_count * 8), 256, 0, st>>>(
             d_offsets, n, tile_prefix, tiles);
@@ -496,35 +497,64 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         bp.tile_prefix = tile_prefix; bp.tiles = tiles;
         bp.pool = (uint16_t *)h->ws_pool.p; bp.runs = (uint32_t *)h->ws_runs.p; bp.totals = tot;
         bp.k = (uint32_t)h->k; bp.nseg = (uint32_t)nseg; bp.log2_seg = log2_seg;
-        {
-            void (*kern)(const BucketParams) = canonical ? bucket_kernel<true> : bucket_kernel<false>;
-            int per_sm = 1;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BK_WARPS * 32, 0));
-            const uint64_t grid = std::min<uint64_t>((uint64_t)h->sm_count * std::max(per_sm, 1), ntiles_bound);
-            kern<<<(unsigned)grid, BK_WARPS * 32, 0, st>>>(bp);
-            CU(cudaGetLastError());
-            h->stats.launches++;
-        }
         CountParams cp{};
         cp.tile_prefix = tile_prefix; cp.pool = bp.pool; cp.runs = bp.runs; cp.totals_in = tot;
-        cp.totals_out = d_totals; cp.out = d_out; cp.counter = h->d_counters + 10;
+        cp.totals_out = d_totals; cp.out = d_out;
         cp.rank_tab = h->d_wave_tab; cp.tab_words = h->wave_tab_words;
         cp.n = n; cp.dim = dim; cp.nseg = (uint32_t)nseg; cp.log2_seg = log2_seg;
         cp.norm_mode = norm_mode; cp.canonical = canonical;
-        {
-            const bool nrm = norm_mode != NORM_COUNTS;
-            void (*kern)(const CountParams) =
-                canonical ? (nrm ? count_kernel<OUT, true, true> : count_kernel<OUT, false, true>)
-                          : (nrm ? count_kernel<OUT, true, false> : count_kernel<OUT, false, false>);
-            const size_t S = (size_t)1 << log2_seg;
-            const size_t smem = (S + 2 * (S / 32)) * 4;
-            if (int rc = set_smem(kern, smem)) return rc;
-            int per_sm = 1;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CK_THREADS, smem));
-            const uint64_t grid = std::min<uint64_t>((uint64_t)h->sm_count * std::max(per_sm, 1), ((n + CK_SEQ_CHUNK - 1) / CK_SEQ_CHUNK) * nseg);
-            kern<<<(unsigned)grid, CK_THREADS, smem, st>>>(cp);
+        void (*bkern)(const BucketParams) = canonical ? bucket_kernel<true> : bucket_kernel<false>;
+        const bool nrm = norm_mode != NORM_COUNTS;
+        void (*ckern)(const CountParams) =
+            canonical ? (nrm ? count_kernel<OUT, true, true> : count_kernel<OUT, false, true>)
+                      : (nrm ? count_kernel<OUT, true, false> : count_kernel<OUT, false, false>);
+        const size_t S = (size_t)1 << log2_seg;
+        const size_t csmem = (S + 2 * (S / 32)) * 4;
+        if (int rc = set_smem(ckern, csmem)) return rc;
+        int b_per_sm = 1, c_per_sm = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b_per_sm, bkern, BK_WARPS * 32, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_per_sm, ckern, CK_THREADS, csmem));
+        // Waves: bucket_kernel is bound by the integer pipe, count_kernel by latency and the row writes.  The batch is
+        // cut into waves of sequences; bucket_kernel(w+1) runs on one helper stream while count_kernel(w) runs on the
+        // other, two CTAs of each per SM, so the two kinds of work share the SMs instead of following each other.
+        const uint64_t nchunks = (n + CK_SEQ_CHUNK - 1) / CK_SEQ_CHUNK;
+        const uint64_t nwaves = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(1, h->bucket_waves), nchunks / 16));
+        if (int rc = h->ws_wavectr.ensure(nwaves * sizeof(unsigned long long))) return rc;
+        CU(cudaMemsetAsync(h->ws_wavectr.p, 0, nwaves * sizeof(unsigned long long), st));
+        CU(cudaEventRecord(h->aux_ev[2], st));
+        cudaStream_t sb = nwaves > 1 ? h->aux[0] : st, sc = nwaves > 1 ? h->aux[1] : st;
+        if (nwaves > 1) {
+            CU(cudaStreamWaitEvent(sb, h->aux_ev[2], 0));
+            CU(cudaStreamWaitEvent(sc, h->aux_ev[2], 0));
+        }
+        const int b_ctas = nwaves > 1 ? std::min(b_per_sm, 2) : b_per_sm;
+        for (uint64_t w = 0; w < nwaves; ++w) {
+            const uint64_t c_lo = nchunks * w / nwaves, c_hi = nchunks * (w + 1) / nwaves;
+            bp.seq_lo = std::min(n, c_lo * CK_SEQ_CHUNK); bp.seq_hi = std::min(n, c_hi * CK_SEQ_CHUNK);
+            const uint64_t wave_tiles = (bp.seq_hi - bp.seq_lo) * 2 + (total_bases / tile_bases) / nwaves + 2;   // grid bound only
+            bkern<<<(unsigned)std::min<uint64_t>((uint64_t)h->sm_count * std::max(b_ctas, 1), wave_tiles), BK_WARPS * 32, 0, sb>>>(bp);
             CU(cudaGetLastError());
-            h->stats.launches++;
+            if (nwaves > 1) {
+                if (h->wave_ev.size() <= w) {
+                    cudaEvent_t e = nullptr;
+                    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    h->wave_ev.push_back(e);
+                }
+                CU(cudaEventRecord(h->wave_ev[w], sb));
+                CU(cudaStreamWaitEvent(sc, h->wave_ev[w], 0));
+            }
+            cp.chunk_lo = c_lo; cp.chunk_hi = c_hi;
+            cp.counter = (unsigned long long *)h->ws_wavectr.p + w;
+            const uint64_t units = (c_hi - c_lo) * nseg;
+            ckern<<<(unsigned)std::min<uint64_t>((uint64_t)h->sm_count * std::max(c_per_sm, 1), std::max<uint64_t>(units, 1)), CK_THREADS, csmem, sc>>>(cp);
+            CU(cudaGetLastError());
+            h->stats.launches += 2;
+        }
+        if (nwaves > 1) {
+            CU(cudaEventRecord(h->aux_ev[0], sb));
+            CU(cudaEventRecord(h->aux_ev[1], sc));
+            CU(cudaStreamWaitEvent(st, h->aux_ev[0], 0));
+            CU(cudaStreamWaitEvent(st, h->aux_ev[1], 0));
         }
         return KTB_OK;
     }
@@ -923,6 +953,8 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     h->ws_tiles.release();
     h->ws_pool.release();
     h->ws_runs.release();
+    h->ws_wavectr.release();
+    for (auto &e : h->wave_ev) if (e) cudaEventDestroy(e);
     if (h->d_rank_full) cudaFree(h->d_rank_full);
     if (h->d_canon_of_rank) cudaFree(h->d_canon_of_rank);
     if (h->d_canon_perm) cudaFree(h->d_canon_perm);
@@ -989,6 +1021,9 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->fwd_min_len = value;
     } else if (!strcmp(key, "bucket")) {
         h->bucket = (int)value;
+    } else if (!strcmp(key, "bucket_waves")) {
+        if (value < 1 || value > 64) return fail(KTB_ERR_ARG, "bucket_waves must be in 1..64");
+        h->bucket_waves = (int)value;
     } else if (!strcmp(key, "bucket_log2_seg")) {
         if (value < 13 || value > 14) return fail(KTB_ERR_ARG, "bucket_log2_seg must be 13 or 14");
         h->bucket_log2_seg = (int)value;

@@ -56,6 +56,7 @@ struct BucketParams {
     uint32_t k;
     uint32_t nseg;
     uint32_t log2_seg;               // codes per segment = 1 << log2_seg
+    uint64_t seq_lo, seq_hi;         // this launch buckets the tiles of sequences [seq_lo, seq_hi) (one wave)
 };
 
 // chunks (16 aligned bytes) touched by sequence [a, b); 0 when it is shorter than k
@@ -138,12 +139,13 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
 
     // tiles cost the same, so they are dealt out statically (tile b, b + grid, ...): the next tile's record and bases
     // are loaded while the current tile is processed; no work counter, no load on the critical path
-    uint64_t tile_id = blockIdx.x;
-    if (tile_id >= ntiles) return;
+    const uint64_t tile_end = p.tile_prefix[p.seq_hi];
+    uint64_t tile_id = (uint64_t)p.tile_prefix[p.seq_lo] + blockIdx.x;
+    if (tile_id >= tile_end) return;
     TileInfo ti = p.tiles[tile_id];
     uint4 v = load_chunk(ti);
-    for (; tile_id < ntiles; tile_id += gridDim.x) {
-        const bool more = tile_id + gridDim.x < ntiles;
+    for (; tile_id < tile_end; tile_id += gridDim.x) {
+        const bool more = tile_id + gridDim.x < tile_end;
         TileInfo nti = ti;
         if (more) nti = p.tiles[tile_id + gridDim.x];
         if (tid == 0) s_tot = 0;
@@ -264,6 +266,7 @@ struct CountParams {
     uint32_t log2_seg;
     int norm_mode;
     int canonical;
+    uint64_t chunk_lo, chunk_hi;   // this launch serves the chunks (of CK_SEQ_CHUNK sequences) [chunk_lo, chunk_hi) (one wave)
 };
 
 constexpr int CK_SEQ_CHUNK = 8;   // consecutive sequences that share one load of a segment's rank tables
@@ -290,8 +293,7 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
     const uint32_t qw = tid >> 3, ql = tid & 7;          // quarter-warp (one per run), lane in it (16 bytes = 8 codes per load)
     constexpr uint32_t NQW = CK_THREADS / 8;
     const uint32_t ntiles = p.tile_prefix[p.n];
-    const uint64_t nchunks = (p.n + CK_SEQ_CHUNK - 1) / CK_SEQ_CHUNK;
-    const uint64_t nunits = nchunks * p.nseg;
+    const uint64_t nunits = (p.chunk_hi - p.chunk_lo) * p.nseg;
     // units differ in cost (segments hold between none and twice the average number of k-mers), so they are dealt out
     // dynamically; the counter is read one unit ahead to keep its round trip off the critical path
     unsigned long long next_unit = 0;
@@ -305,8 +307,8 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
         __syncthreads();
         const unsigned long long unit = s_unit;
         if (unit >= nunits) break;
-        const uint64_t chunk = unit / p.nseg;
-        const uint32_t seg = (uint32_t)(unit - chunk * p.nseg);
+        const uint64_t chunk = p.chunk_lo + unit / p.nseg;
+        const uint32_t seg = (uint32_t)(unit % p.nseg);
         uint64_t col0, col1;   // columns of this segment
         if constexpr (CANON) {
             const uint32_t *gpref = p.rank_tab + p.tab_words;

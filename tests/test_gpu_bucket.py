@@ -93,3 +93,15 @@ def test_config5ii_all_sequences_bit_exact():
         assert np.array_equal(ht[a:b], wt)
         assert_rows_equal(counts[a:b].cpu().numpy().view(np.uint32), want, np.uint32, f"config 5ii rows {a}..{b}")
     oc.close()
+
+
+@pytest.mark.parametrize("waves", [1, 3, 8, 64])
+def test_bucket_waves_agree(waves):
+    """bucket_kernel(w+1) overlaps count_kernel(w) on two streams: any number of waves gives the same rows (wave
+    boundaries fall on chunks of 8 sequences; the last wave is ragged)."""
+    rng = np.random.default_rng(31)
+    lengths = np.r_[rng.integers(0, 9000, size=300), [0, 8, 9, 10, 50_000], rng.integers(3000, 5000, size=133)]
+    bases, offsets = random_batch(rng, lengths, noise=0.002, n_runs=0.1)
+    check(9, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"k9 {waves} waves", bucket_waves=waves)
+    check(9, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, what=f"k9 {waves} waves f32", bucket_waves=waves)
+    check(8, bases, offsets, mins=False, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"raw k8 {waves} waves", bucket_waves=waves)

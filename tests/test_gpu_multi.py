@@ -91,3 +91,54 @@ def test_current_device_is_restored():
     x = torch.ones(4, device="cuda")
     assert x.device.index == 0
     oc.close()
+
+
+def _rank_worker(rank: int, world: int, port: int, ret):
+    """One process per rank as under torchrun: every rank computes ITS contiguous range on a GPU (rank % #GPUs, so two
+    ranks share the device of a 1-GPU box), ranks exchange only bookkeeping (gloo)."""
+    import os
+    import torch.distributed as dist
+    import torch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kmertools_b200.shard import local_batch
+        rng = np.random.default_rng(123)   # the same batch on every rank (as a shared input file would be)
+        lengths = np.r_[rng.integers(0, 400, size=300), [50_000, 0, 0, 7], rng.integers(100, 3000, size=100)]
+        bases, offsets = random_batch(rng, lengths, noise=0.01)
+        lb, lo_offs, lo, hi = local_batch(bases, offsets, world, rank)
+        b = shard_bounds(offsets, world)
+        assert (lo, hi) == (int(b[rank]), int(b[rank + 1]))          # python sharder == library partition
+        oc = OligoComputer(5, device=rank % ndev())
+        rows = oc.vectorise_packed(lb, lo_offs, norm_mode=NORM_CLI, dtype=np.float32)
+        assert oc.stats()["launches"] > 0
+        full, _ = O.vectorise_batch(bases, offsets, 5, True, NORM_CLI)
+        assert_rows_equal(rows, full[lo:hi], np.float32, f"rank {rank}")
+        t = torch.tensor([lo, hi], dtype=torch.int64)
+        got = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(got, t)
+        ranges = [tuple(int(x) for x in g) for g in got]
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(lengths) and all(a[1] == c[0] for a, c in zip(ranges, ranges[1:]))
+        oc.close()
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_compute_their_shards_on_gpus():
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    world = 2
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        ret = mgr.dict()
+        procs = [ctx.Process(target=_rank_worker, args=(r, world, port, ret)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=300)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        assert dict(ret) == {0: True, 1: True}
