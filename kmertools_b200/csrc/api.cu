@@ -137,7 +137,7 @@ struct ktb_oligo {
     int fwd_fold = 1;     // long_kernel MODE_FWD (3 <= k <= 6 canonical, long sequences, u32 / f32 rows)
     int64_t fwd_min_len = 1024;   // mean sequence length from which MODE_FWD replaces seq_kernel mode 1
     int bucket = 1;       // rows larger than shared memory: bucket_kernel + count_kernel instead of global atomics
-    int bucket_waves = 8;       // waves of that path (bucket_kernel of wave w+1 overlaps count_kernel of wave w)
+    int bucket_waves = 1;       // waves of that path (bucket_kernel of wave w+1 overlaps count_kernel of wave w); measured: 1 is best
     int bucket_log2_seg = 14;   // columns per segment of that path (2^14 u32 bins = 64 KB of shared memory)
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
     int global_steps_per_warp = 1;
@@ -514,9 +514,11 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         int b_per_sm = 1, c_per_sm = 1;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b_per_sm, bkern, BK_WARPS * 32, 0));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_per_sm, ckern, CK_THREADS, csmem));
-        // Waves: bucket_kernel is bound by the integer pipe, count_kernel by latency and the row writes.  The batch is
-        // cut into waves of sequences; bucket_kernel(w+1) runs on one helper stream while count_kernel(w) runs on the
-        // other, two CTAs of each per SM, so the two kinds of work share the SMs instead of following each other.
+        // Waves (option "bucket_waves", default 1): bucket_kernel is bound by the integer pipe, count_kernel by latency and
+        // the row writes, so the batch can be cut into waves with bucket_kernel(w+1) on one helper stream and
+        // count_kernel(w) on the other, sharing the SMs.  Measured on config 5ii (profiles/r2_sweeps.txt, batch r2i):
+        // 1.57 ms with one wave, 1.63 - 1.77 ms with 2 - 16 — the two kernels take each other's shared memory and
+        // registers and both lose more occupancy than the overlap returns.  Kept as an option.
         const uint64_t nchunks = (n + CK_SEQ_CHUNK - 1) / CK_SEQ_CHUNK;
         const uint64_t nwaves = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(1, h->bucket_waves), nchunks / 16));
         if (int rc = h->ws_wavectr.ensure(nwaves * sizeof(unsigned long long))) return rc;
