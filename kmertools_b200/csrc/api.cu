@@ -134,6 +134,7 @@ struct ktb_oligo {
     int even_rank = 1;    // use seq_kernel mode 7 where it applies
     int long_warps = 0;   // warps per CTA of long_kernel: 0 = from the mean sequence length, else 4 or 8
     int k7_mid = 1;       // long_kernel MODE_K7 (k = 7 canonical, u32 / f32 rows)
+    int fwd_replicas = 1; // MODE_FWD on long contigs: lane-private replicas of the bins (k <= 5)
     int fwd_fold = 1;     // long_kernel MODE_FWD (3 <= k <= 6 canonical, long sequences, u32 / f32 rows)
     int64_t fwd_min_len = 1024;   // mean sequence length from which MODE_FWD replaces seq_kernel mode 1
     int bucket = 1;       // rows larger than shared memory: bucket_kernel + count_kernel instead of global atomics
@@ -329,6 +330,7 @@ int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
         int nw = h->long_warps > 0 ? h->long_warps : (mode == MODE_K7 ? (mean_len <= 32768 ? 10 : 8) : (mean_len <= 32768 ? 4 : 8));
         if (nw == 10 && mode != MODE_K7) nw = 8;
         void (*kern)(const LongParams) = nullptr;
+        int rs = 0;
         if (mode == MODE_K7) {
             if (nw == 4) kern = nrm ? long_kernel<OUT, true, MODE_K7, 4> : long_kernel<OUT, false, MODE_K7, 4>;
             else if (nw == 10) kern = nrm ? long_kernel<OUT, true, MODE_K7, 10> : long_kernel<OUT, false, MODE_K7, 10>;
@@ -336,8 +338,16 @@ int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
         } else {
             if (nw == 4) kern = nrm ? long_kernel<OUT, true, MODE_FWD, 4> : long_kernel<OUT, false, MODE_FWD, 4>;
             else kern = nrm ? long_kernel<OUT, true, MODE_FWD, 8> : long_kernel<OUT, false, MODE_FWD, 8>;
+            // long contigs at k <= 5: lane-private replicas of the (few) bins, k folded into immediates
+            if (h->fwd_replicas && mean_len >= 32768 && nw == 8) {
+                if (p.k == 3) { kern = nrm ? long_kernel<OUT, true, MODE_FWD, 8, 3, 5> : long_kernel<OUT, false, MODE_FWD, 8, 3, 5>; rs = 5; }
+                if (p.k == 4) { kern = nrm ? long_kernel<OUT, true, MODE_FWD, 8, 4, 5> : long_kernel<OUT, false, MODE_FWD, 8, 4, 5>; rs = 5; }
+                if (p.k == 5) { kern = nrm ? long_kernel<OUT, true, MODE_FWD, 8, 5, 3> : long_kernel<OUT, false, MODE_FWD, 8, 5, 3>; rs = 3; }
+            }
         }
-        const size_t smem = ((((size_t)p.hist_words + 31) & ~(size_t)31) + p.dim) * 4;
+        LongParams q = p;
+        if (rs) q.hist_words = (((uint32_t)1 << (2 * p.k)) << rs) + (1u << rs);   // + the always-zero replicas (rc slot of palindromes)
+        const size_t smem = ((((size_t)q.hist_words + 31) & ~(size_t)31) + p.dim) * 4;
         if (int rc = set_smem(kern, smem)) return rc;
         int per_sm = 1;
         const int threads = nw * 32;
@@ -347,7 +357,6 @@ int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
         const uint64_t nitems = ((p.n + SHORT_G - 1) / SHORT_G) * SHORT_G;
         if (grid > nitems) grid = nitems;
         if (grid < 1) grid = 1;
-        LongParams q = p;
         q.grab = h->seq_grab > 0 ? (uint32_t)h->seq_grab
                                  : (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(16, 4096 / std::max<uint64_t>(mean_len, 1)));
         kern<<<(unsigned)grid, threads, smem, st>>>(q);
@@ -1017,6 +1026,8 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->long_warps = (int)value;
     } else if (!strcmp(key, "k7_mid")) {
         h->k7_mid = (int)value;
+    } else if (!strcmp(key, "fwd_replicas")) {
+        h->fwd_replicas = (int)value;
     } else if (!strcmp(key, "fwd_fold")) {
         h->fwd_fold = (int)value;
     } else if (!strcmp(key, "fwd_min_len")) {

@@ -9,7 +9,7 @@
 //   row[rank(min(f,r))] += 1  (canonical)   |   row[f] += 1  (raw)          for every valid p
 //   row[j]   /= max(1, total)                      when normalising
 //
-// Kernels:
+// Kernels of this file (long_kernel.cuh and bucket_kernels.cuh hold the round-2 kernels):
 //   short_kernel  : one WARP per group of 16 short reads (<= 255 windows each, 4^k <= 1024): read-aligned
 //                   16-base chunks per lane, byte counters packed four to a word, shared-memory atomics,
 //                   linear coalesced write-out with fused normalisation.  Groups it cannot take go to a
@@ -17,9 +17,13 @@
 //   seq_kernel    : one CTA per sequence (consumes the reject list, or everything when k is large): warps walk
 //                   contiguous runs of 32-chunk steps with a carried look-back word; histogram in shared
 //                   memory in code space (mode 1), dense middle-base space (mode 4, k = 7), rank space
-//                   (mode 2, k = 8), packed 16-bit code space (mode 5, optional), raw (mode 0), or straight
+//                   (mode 2 / 7, k = 8), packed 16-bit rank space (mode 5), raw (mode 0), or straight
 //                   into zeroed global rows with RED atomics for histograms larger than shared memory
-//                   (mode 3, driven in L2-sized waves by the host).
+//                   (mode 3, driven in L2-sized waves by the host).  long_kernel replaces it for k = 7 and for
+//                   long sequences at k <= 5 (u32 / f32 rows).
+//   wave_kernel   : rows larger than shared memory as ONE persistent cooperative launch (global RED atomics in
+//                   L2-sized waves).  Round 2 replaced it by bucket_kernel + count_kernel for k <= 10; it stays
+//                   the path for k = 11, 12 and behind the option bucket = 0.
 //   finalize_kernel: u32 counts -> f32 / f64 rows for mode 3.
 //   flat_kernel   : flat decomposition of the base stream + global atomics; cross-check only (force_path=1).
 #pragma once
@@ -121,18 +125,26 @@ __device__ __forceinline__ void decode16(const uint4 v, uint32_t &cf, uint32_t &
     const uint32_t u23 = __byte_perm(m[3], m[2], 0x0073);
     cf = __byte_perm(u23, u01, 0x5410);
     vm = 0xFFFFu;
-    if (!all_ok) {  // rare: N / IUPAC / U / raw 0..3 codes — exact per-byte path
-        cf = 0;
+    if (!all_ok) {  // N / IUPAC / U / raw 0..3 codes somewhere in the warp: exact path, four bytes at a time
+        // zero-byte detector: bit 7 of every byte of the result is set iff that byte of x is 0
+        auto zero_bytes = [](uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; };
         vm = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t c = nt4_code((w[q] >> (8 * j)) & 0xFFu);
-                cf = (cf << 2) | (c & 3u);
-                vm = (vm << 1) | (c < 4u ? 1u : 0u);
-            }
+            const uint32_t u = w[q] & 0xDFDFDFDFu;
+            uint32_t c4 = ((w[q] >> 1) ^ (w[q] >> 2)) & 0x03030303u;          // right for A C G T U, either case
+            const uint32_t y = (c4 | (c4 >> 4)) & 0x00FF00FFu;
+            const uint32_t recon = __byte_perm(0x54474341u, 0u, (y | (y >> 8)) & 0xFFFFu);
+            const uint32_t raw = zero_bytes(w[q] & 0xFCFCFCFCu);               // bytes 0..3 are their own code
+            const uint32_t ok = zero_bytes(recon ^ u) | zero_bytes(u ^ 0x55555555u) | raw;
+            const uint32_t rawff = (raw >> 7) * 0xFFu;
+            c4 = (c4 & ~rawff) | (w[q] & 0x03030303u & rawff);
+            m[q] = c4 * 0x40100401u;
+            vm = (vm << 4) | ((((ok >> 7) * 0x08040201u) >> 24) & 0xFu);       // first base of the word = highest bit
         }
+        const uint32_t v01 = __byte_perm(m[1], m[0], 0x0073);
+        const uint32_t v23 = __byte_perm(m[3], m[2], 0x0073);
+        cf = __byte_perm(v23, v01, 0x5410);
     }
 }
 

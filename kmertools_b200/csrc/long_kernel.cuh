@@ -108,7 +108,7 @@ __device__ __forceinline__ void k7_keys_phase(uint32_t cf, uint32_t cf_prev, uin
 
 // ---- write-out of one row into the row image (normalisation fused), histogram re-initialised on the way.
 // SMALL: every count and the divisor are below 2^23 (exact in f32, magic-constant conversion valid).
-template <int OUT, bool NORM, int MODE, int NW, bool SMALL>
+template <int OUT, bool NORM, int MODE, int NW, bool SMALL, int RS>
 __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hbytes, uint32_t *stage, uint64_t dv) {
     using T = typename OutT<OUT>::type;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -168,7 +168,7 @@ __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hby
                 move4(b);
             }
         }
-    } else {
+    } else if constexpr (RS == 0) {
         for (uint32_t j = tid; j < p.dim; j += NW * 32) {
             const uint32_t e = __ldg(p.sched + j);
             uint32_t *a = reinterpret_cast<uint32_t *>(hbytes + (e & 0xFFFFu));
@@ -178,10 +178,30 @@ __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hby
             *b = 0;
             reinterpret_cast<T *>(stage)[j] = cvt_count<OUT, NORM, SMALL>(cnt, dF, rinv, dD);
         }
+    } else {
+        // 2^RS lane-private replicas per bin (bin c, replica r at byte (c << (2 + RS)) + 4 r): a column is the sum of the
+        // replicas of c and of rc(c); lane l starts at replica l so the 32 lanes of a load hit 32 banks
+        constexpr uint32_t R = 1u << RS;
+        for (uint32_t j = tid; j < p.dim; j += NW * 32) {
+            const uint32_t e = __ldg(p.sched + j);
+            const uint32_t ca = (e & 0xFFFFu) << RS, cb = (e >> 16) << RS;
+            uint32_t cnt = 0;
+#pragma unroll 8
+            for (uint32_t r = 0; r < R; ++r) {
+                const uint32_t rr = ((r + lane) & (R - 1u)) << 2;
+                cnt += *reinterpret_cast<const uint32_t *>(hbytes + ca + rr) + *reinterpret_cast<const uint32_t *>(hbytes + cb + rr);
+            }
+            reinterpret_cast<T *>(stage)[j] = cvt_count<OUT, NORM, SMALL>(cnt, dF, rinv, dD);
+        }
+        __syncthreads();   // every column has read its bins: clear them with a linear sweep
+        for (uint32_t i = tid * 4u; i < p.hist_words; i += NW * 32 * 4u) *reinterpret_cast<uint4 *>(hbytes + 4u * i) = make_uint4(0, 0, 0, 0);
     }
 }
 
-template <int OUT, bool NORM, int MODE, int NW>
+// KT: compile-time k of MODE_FWD (0 = p.k); RS: log2 of the lane-private replicas per bin (MODE_FWD, long contigs:
+// k <= 4 has so few bins that the 32 lanes of an atomic keep hitting the same banks — 3.9 wavefronts per ATOMS on
+// config 4 — so bin c of lane l lives at word (c << RS) + (l mod 2^RS): one wavefront per ATOMS, folded at write-out)
+template <int OUT, bool NORM, int MODE, int NW, int KT = 0, int RS = 0>
 __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 8)) long_kernel(const LongParams p) {
     static_assert(OUT == OUT_U32 || OUT == OUT_F32, "f64 rows keep seq_kernel");
     static_assert(NW == 4 || NW == 8 || NW == 10, "warps per CTA");
@@ -207,9 +227,10 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
     if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
     __syncthreads();
 
-    const uint32_t k = (MODE == MODE_K7) ? 7u : p.k;
-    const uint32_t kmask4 = ((1u << (2 * k)) - 1u) << 2;
-    (void)kmask4;
+    const uint32_t k = (MODE == MODE_K7) ? 7u : (KT ? (uint32_t)KT : p.k);
+    const uint32_t kmaskR = ((1u << (2 * k)) - 1u) << (2 + RS);            // code pre-scaled to the byte offset of its bin
+    const uint32_t lane_off = ((uint32_t)lane & ((1u << RS) - 1u)) << 2;   // this lane's replica
+    (void)kmaskR; (void)lane_off;
     using T = typename OutT<OUT>::type;
     T *out = reinterpret_cast<T *>(p.out);
     const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
@@ -287,8 +308,12 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
                         } else {
                             const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
 #pragma unroll
-                            for (int e = 0; e < 16; ++e)
-                                off[e] = (e < 15) ? ((uint32_t)(F64 >> (2 * (14 - e))) & kmask4) : ((cf << 2) & kmask4);
+                            for (int e = 0; e < 16; ++e) {
+                                constexpr int up = 2 + RS;                       // window e sits at bit 2 (15 - e) of F64
+                                const int sh = 2 * (15 - e) - up;
+                                const uint32_t x = sh >= 0 ? (uint32_t)(F64 >> (sh >= 0 ? sh : 0)) : (cf << (sh < 0 ? -sh : 0));
+                                off[e] = (x & kmaskR) | lane_off;
+                            }
                         }
                         if (__all_sync(FULL, vw == 0xFFFFu)) {
 #pragma unroll
@@ -316,8 +341,8 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
             ++it;
             const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
             if (tid == 0 && p.totals) p.totals[seq] = total;
-            if (dv < (1ULL << 23)) long_write_row<OUT, NORM, MODE, NW, true>(p, hbytes, stage, dv);
-            else long_write_row<OUT, NORM, MODE, NW, false>(p, hbytes, stage, dv);
+            if (dv < (1ULL << 23)) long_write_row<OUT, NORM, MODE, NW, true, RS>(p, hbytes, stage, dv);
+            else long_write_row<OUT, NORM, MODE, NW, false, RS>(p, hbytes, stage, dv);
             fence_async_smem();
             __syncthreads();
             if (tid == 0) bulk_store(out + seq * (uint64_t)p.dim, stage, p.dim * 4u);

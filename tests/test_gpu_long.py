@@ -80,3 +80,23 @@ def test_forward_fold_contigs_default_dispatch(k):
     offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
     offsets[1:] = np.cumsum([len(s) for s in seqs])
     check(k, bases, offsets, dtype=np.float32, what=f"low complexity k{k}")
+
+
+@pytest.mark.parametrize("k", [3, 4, 5])
+def test_forward_fold_replicated_bins(k):
+    """Long contigs (mean length >= 32 kbp) at k <= 5 count into lane-private replicas of the bins (32 at k <= 4, 8 at
+    k = 5) that are summed at write-out; same rows as without replicas and as the oracle, palindromes included."""
+    rng = np.random.default_rng(60 + k)
+    lengths = np.r_[np.exp(rng.uniform(np.log(2e4), np.log(4e5), size=24)).astype(np.int64), [0, 3, k - 1, k, 700, 33_000]]
+    rng.shuffle(lengths)
+    bases, offsets = random_batch(rng, lengths, noise=0.004, n_runs=0.8)
+    for dtype, norm in ((np.uint32, NORM_COUNTS), (np.float32, NORM_CLI), (np.float32, NORM_PY)):
+        a = check(k, bases, offsets, norm_mode=norm, dtype=dtype, what=f"replicas k{k}", fwd_replicas=1)
+        b = check(k, bases, offsets, norm_mode=norm, dtype=dtype, what=f"plain k{k}", fwd_replicas=0)
+        assert np.array_equal(a, b)
+    seqs = [b"A" * 500_000, b"ACGT" * 100_000, b"GC" * 200_000 + b"N" * 1000 + b"TTAA" * 50_000]   # hot bins, palindromes
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    check(k, bases, offsets, dtype=np.float32, what=f"replicas low complexity k{k}")
+    check(k, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"replicas low complexity k{k} counts")
