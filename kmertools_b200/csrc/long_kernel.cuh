@@ -277,15 +277,14 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
                         return __ldg(seq_chunks + c);
                     };
                     // two steps of bases in flight per warp (HBM latency is longer than one step of work at 24 warps/SM)
-                    uint4 vnext = fetch(w0 + lane);
-                    uint4 vnext2 = fetch(w0 + 32 + lane);
-                    for (uint32_t c0 = w0; c0 < w1; c0 += 32) {
+                    // (two buffers used alternately, each reloaded right after it has been decoded: no register copies)
+                    uint4 buf_a = fetch(w0 + lane);
+                    uint4 buf_b = fetch(w0 + 32 + lane);
+                    auto do_step = [&](uint4 &buf, const uint32_t c0) {
                         const uint32_t c = c0 + lane;
-                        const uint4 v = vnext;
-                        vnext = vnext2;
-                        if (c0 + 64 < w1) vnext2 = fetch(c + 64);
                         uint32_t cf, vm;
-                        decode16(v, cf, vm);
+                        decode16(buf, cf, vm);
+                        if (c0 + 64 < w1) buf = fetch(c + 64);
                         if (c >= w1) { vm = 0; cf = (uint32_t)lane * 0x9E3779B1u; }   // idle lanes add 0 at scattered bins
                         if (c == 0) vm &= head_mask;
                         if (c == nch - 1) vm &= tail_mask;
@@ -327,6 +326,10 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
                             for (int e = 0; e < 16; ++e)   // branch-free: an invalid window adds 0
                                 atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), (vw >> (15 - e)) & 1u);
                         }
+                    };
+                    for (uint32_t c0 = w0; c0 < w1; c0 += 64) {
+                        do_step(buf_a, c0);
+                        if (c0 + 32 < w1) do_step(buf_b, c0 + 32);
                     }
                 }
             }
