@@ -138,6 +138,7 @@ struct ktb_oligo {
     int fwd_fold = 1;     // long_kernel MODE_FWD (3 <= k <= 6 canonical, long sequences, u32 / f32 rows)
     int64_t fwd_min_len = 1024;   // mean sequence length from which MODE_FWD replaces seq_kernel mode 1
     int bucket = 1;       // rows larger than shared memory: bucket_kernel + count_kernel instead of global atomics
+    int bucket_hist_kb = 64;    // histogram memory of count_kernel per CTA: 64 KB (three CTAs per SM) or 96 KB (two)
     int bucket_waves = 1;       // waves of that path (bucket_kernel of wave w+1 overlaps count_kernel of wave w); measured: 1 is best
     int bucket_log2_seg = 14;   // columns per segment of that path (2^14 u32 bins = 64 KB of shared memory)
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
@@ -325,9 +326,10 @@ int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
         const uint64_t mean_len = p.total_bases / std::max<uint64_t>(p.n, 1);
         // 4 warps per CTA for reads of a few steps per warp (10 kbp = 20 steps: 5 per warp, balanced, half the per-warp
         // set-up of 8 warps); 8 warps for long contigs
-        // measured (profiles/r2_sweeps.txt): k = 7 rows want as many warps as fit (10 per CTA, three CTAs per SM of
-        // 64 KB each; 10 divides the 20 steps of a 10 kbp read); the small histograms of k <= 5 run best with 4 warps
-        int nw = h->long_warps > 0 ? h->long_warps : (mode == MODE_K7 ? (mean_len <= 32768 ? 10 : 8) : (mean_len <= 32768 ? 4 : 8));
+        // measured (profiles/r2_sweeps.txt): k = 7 rows ran best with 10 warps per CTA (three CTAs per SM of 64 KB each)
+        // until the kernel looked ahead across sequences; that needs 72 registers, which 8 warps have and 10 do not
+        // (799 against 765 Gbases/s on config 3).  The small histograms of k <= 5 run best with 4 warps
+        int nw = h->long_warps > 0 ? h->long_warps : (mode == MODE_K7 ? (mean_len < 1024 ? 10 : 8) : (mean_len <= 32768 ? 4 : 8));
         if (nw == 10 && mode != MODE_K7) nw = 8;
         void (*kern)(const LongParams) = nullptr;
         int rs = 0;
@@ -512,13 +514,20 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         cp.rank_tab = h->d_wave_tab; cp.tab_words = h->wave_tab_words;
         cp.n = n; cp.dim = dim; cp.nseg = (uint32_t)nseg; cp.log2_seg = log2_seg;
         cp.norm_mode = norm_mode; cp.canonical = canonical;
+#ifdef KTB_COUNT_PROBE
+        if (const char *e = getenv("KTB_COUNT_PROBE")) cp.probe = (uint32_t)atoi(e);
+#endif
         void (*bkern)(const BucketParams) = canonical ? bucket_kernel<true> : bucket_kernel<false>;
         const bool nrm = norm_mode != NORM_COUNTS;
         void (*ckern)(const CountParams) =
             canonical ? (nrm ? count_kernel<OUT, true, true> : count_kernel<OUT, false, true>)
                       : (nrm ? count_kernel<OUT, true, false> : count_kernel<OUT, false, false>);
+        // histogram memory: 64 KB either way — one buffer of 2^14 bins (segments with at most half as many columns
+        // alternate between its halves) or two buffers of 2^13
         const size_t S = (size_t)1 << log2_seg;
-        const size_t csmem = (S + 2 * (S / 32)) * 4;
+        cp.hist_words = (uint32_t)(log2_seg < 14 ? 2 * S : S);
+        if (h->bucket_hist_kb == 96) cp.hist_words = 24576;   // segments of up to 12,288 columns alternate between two halves
+        const size_t csmem = ((size_t)cp.hist_words + 2 * (S / 32)) * 4;
         if (int rc = set_smem(ckern, csmem)) return rc;
         int b_per_sm = 1, c_per_sm = 1;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b_per_sm, bkern, BK_WARPS * 32, 0));
@@ -1034,6 +1043,9 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->fwd_min_len = value;
     } else if (!strcmp(key, "bucket")) {
         h->bucket = (int)value;
+    } else if (!strcmp(key, "bucket_hist_kb")) {
+        if (value != 64 && value != 96) return fail(KTB_ERR_ARG, "bucket_hist_kb must be 64 or 96");
+        h->bucket_hist_kb = (int)value;
     } else if (!strcmp(key, "bucket_waves")) {
         if (value < 1 || value > 64) return fail(KTB_ERR_ARG, "bucket_waves must be in 1..64");
         h->bucket_waves = (int)value;

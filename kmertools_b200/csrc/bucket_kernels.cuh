@@ -31,7 +31,8 @@ namespace ktb {
 constexpr int BK_WARPS = 8;                  // bucket_kernel: 256 threads, one 31-chunk step per warp
 constexpr int BK_CHUNKS_PER_STEP = 31;       // lane 0 of a step only provides the look-back chunk
 constexpr int BK_TILE_CHUNKS = BK_WARPS * BK_CHUNKS_PER_STEP;       // 248 chunks = 3,968 bases (positions fit 12 bits)
-constexpr int BK_MAX_SEG = 64;
+constexpr int BK_MAX_SEG = 128;
+constexpr int BK_SEG_PER_LANE = BK_MAX_SEG / 32;   // phase 2: one warp scans the segment counters
 constexpr int BK_TILE_CAP = BK_TILE_CHUNKS * 16 + BK_MAX_SEG * 8;   // pool entries per tile (runs padded to 8 entries)
 constexpr int CK_THREADS = 256;              // count_kernel
 constexpr int CK_WARPS = CK_THREADS / 32;
@@ -205,19 +206,27 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
 
         // ---- phase 2: run bases (16-byte aligned) and descriptors
         if (warp == 0) {
-            const uint32_t c0 = (2 * lane < (int)p.nseg) ? s_cnt[2 * lane] : 0u;
-            const uint32_t c1 = (2 * lane + 1 < (int)p.nseg) ? s_cnt[2 * lane + 1] : 0u;
-            const uint32_t a0 = (c0 + 7u) & ~7u, a1 = (c1 + 7u) & ~7u;
-            uint32_t incl = a0 + a1;
+            uint32_t cn[BK_SEG_PER_LANE], sum = 0;
+#pragma unroll
+            for (int u = 0; u < BK_SEG_PER_LANE; ++u) {
+                const uint32_t sg = BK_SEG_PER_LANE * lane + u;
+                cn[u] = sg < p.nseg ? s_cnt[sg] : 0u;
+                sum += (cn[u] + 7u) & ~7u;
+            }
+            uint32_t incl = sum;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t t = __shfl_up_sync(FULL, incl, d);
                 if (lane >= d) incl += t;
             }
-            const uint32_t b0 = incl - a0 - a1, b1 = b0 + a0;
+            uint32_t b = incl - sum;
             uint32_t *rd = p.runs + tile_id;   // descriptors of one segment are contiguous over the tiles (count_kernel's order)
-            if (2 * lane < (int)p.nseg) { s_base[2 * lane] = b0; rd[(uint64_t)(2 * lane) * ntiles] = ((b0 >> 3) << 16) | c0; }
-            if (2 * lane + 1 < (int)p.nseg) { s_base[2 * lane + 1] = b1; rd[(uint64_t)(2 * lane + 1) * ntiles] = ((b1 >> 3) << 16) | c1; }
+#pragma unroll
+            for (int u = 0; u < BK_SEG_PER_LANE; ++u) {
+                const uint32_t sg = BK_SEG_PER_LANE * lane + u;
+                if (sg < p.nseg) { s_base[sg] = b; rd[(uint64_t)sg * ntiles] = ((b >> 3) << 16) | cn[u]; }
+                b += (cn[u] + 7u) & ~7u;
+            }
             if (lane == 31) s_copy = incl;
             if (lane == 0 && s_tot) atomicAdd(p.totals + ti.seq, (unsigned long long)s_tot);
         }
@@ -264,10 +273,22 @@ struct CountParams {
     uint64_t dim;
     uint32_t nseg;
     uint32_t log2_seg;
+    uint32_t hist_words;           // words of histogram memory: S, or 2 S (every segment alternates between two buffers)
     int norm_mode;
     int canonical;
+#ifdef KTB_COUNT_PROBE
+    uint32_t probe;                // 1 no atomics, 2 no zeroing, 4 no bulk copy, 8 no code loads
+#endif
     uint64_t chunk_lo, chunk_hi;   // this launch serves the chunks (of CK_SEQ_CHUNK sequences) [chunk_lo, chunk_hi) (one wave)
 };
+
+// Diagnostic builds only (tools/gpu_probe_count.sh compiles a second library with -DKTB_COUNT_PROBE): phases of
+// count_kernel can be switched off to attribute its time; the rows such a build writes are wrong by construction.
+#ifdef KTB_COUNT_PROBE
+#define PROBE(bit) ((p.probe & (bit)) != 0)
+#else
+#define PROBE(bit) false
+#endif
 
 constexpr int CK_SEQ_CHUNK = 8;   // consecutive sequences that share one load of a segment's rank tables
 
@@ -282,12 +303,13 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
     extern __shared__ __align__(128) uint32_t csm[];
     __shared__ unsigned long long s_unit;
     __shared__ uint32_t s_tp[CK_SEQ_CHUNK + 1];   // tile prefix of the chunk's sequences
+    __shared__ unsigned long long s_tot[CK_SEQ_CHUNK];   // valid windows of the chunk's sequences
     __shared__ uint32_t s_rd[CK_THREADS];         // descriptor of every quarter-warp's first run, per sequence of the chunk
     static_assert(CK_THREADS == CK_SEQ_CHUNK * (CK_THREADS / 8), "one descriptor slot per (sequence, quarter-warp)");
     using T = typename OutT<OUT>::type;
     const uint32_t S = 1u << p.log2_seg;                 // codes per segment
     const uint32_t wps = S / 32;                         // bitmap words per segment
-    uint32_t *s_bits = csm + S;                          // CANON: bitmap of the segment's canonical codes
+    uint32_t *s_bits = csm + p.hist_words;               // CANON: bitmap of the segment's canonical codes
     uint32_t *s_pref = s_bits + wps;                     // CANON: columns before each word, relative to the segment's first
     const int tid = threadIdx.x;
     const uint32_t qw = tid >> 3, ql = tid & 7;          // quarter-warp (one per run), lane in it (16 bytes = 8 codes per load)
@@ -333,7 +355,7 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
         // iteration i — a whole iteration (count, write-out, wait for the previous bulk copy, zeroing) ahead of their use
         // segments with at most S / 2 columns (the upper half of the code space: fewer and fewer codes are canonical)
         // alternate between the two halves of the histogram memory, so the CTA never waits for its own last bulk copy
-        const bool two = bins * 2u <= S;
+        const bool two = bins * 2u <= p.hist_words;
         if (tid == 0) bulk_wait_read();   // buffers change roles between units
         {
             const uint32_t j = tid >> 5, q = tid & 31;   // CK_THREADS = CK_SEQ_CHUNK * NQW
@@ -341,72 +363,100 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
             s_rd[tid] = (a0 + q < a1) ? __ldg(runs + a0 + q) : 0u;
             if (q == 0) s_tp[j] = a0;
             if (tid == CK_THREADS - 1) s_tp[CK_SEQ_CHUNK] = a1;
+            if (q == 1) s_tot[j] = p.totals_in[min(p.n - 1, seq0 + j)];   // (a load per sequence here would stall every thread)
         }
         __syncthreads();
-        auto first_codes = [&](uint32_t i) -> uint4 {   // this lane's 16 bytes of the first run of the chunk's i-th sequence
+        // this lane's first 2 x 16 bytes of the first run of the chunk's i-th sequence (a run of a 3,968-base tile has ~62
+        // codes at 64 segments: lanes 0..7 of the quarter-warp cover 128 with two loads each, both requested a sequence ahead)
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        auto first_codes = [&](const uint32_t i, uint4 &a, uint4 &b) {
             const uint32_t rdi = s_rd[i * NQW + qw];
-            if (8u * ql >= (rdi & 0xFFFFu)) return make_uint4(0, 0, 0, 0);
-            return __ldg(reinterpret_cast<const uint4 *>(p.pool + (uint64_t)(s_tp[i] + qw) * BK_TILE_CAP + ((uint64_t)(rdi >> 16) << 3)) + ql);
+            const uint32_t c = rdi & 0xFFFFu;
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)(s_tp[i] + qw) * BK_TILE_CAP + ((uint64_t)(rdi >> 16) << 3));
+            a = (8u * ql < c && !PROBE(8)) ? __ldg(src + ql) : zero4;
+            b = (64u + 8u * ql < c && !PROBE(8)) ? __ldg(src + 8 + ql) : zero4;
         };
-        uint4 v = first_codes(0);
+        // add `delta` to the bins of the first `left` of the eight codes in v
+        auto tally = [&](const uint4 v, const uint32_t left, const uint32_t delta, uint32_t *hist) {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e8 = 0; e8 < 8; ++e8) {
+                const uint32_t e = (e8 & 1) ? (w[e8 >> 1] >> 16) : (w[e8 >> 1] & 0xFFFFu);
+                uint32_t col = e;
+                if constexpr (CANON) {
+                    const uint32_t wd = (e >> 5) & (wps - 1u);   // (padding behind a run is arbitrary: stay inside the tables)
+                    col = s_pref[wd] + (uint32_t)__popc(s_bits[wd] & ~(0xFFFFFFFFu << (e & 31u)));
+                }
+                if ((uint32_t)e8 < left && !PROBE(1)) atomicAdd(hist + col, delta);
+            }
+        };
+        auto left_of = [&](const uint32_t cnt, const uint32_t first) -> uint32_t { return cnt > first ? cnt - first : 0u; };
+        // (measured and not kept: u32 rows leave the histogram intact, so the next sequence could UN-COUNT the previous codes
+        // with the same atomics instead of zeroing 64 KB — 1.61 - 1.70 ms against 1.57 ms on config 5ii: the second rank
+        // look-up per code costs more than sixteen conflict-free 128-bit stores per thread)
+        uint4 v0, v1;
+        first_codes(0, v0, v1);
         for (uint64_t seq = seq0; seq < seq_end; ++seq) {
             const uint32_t si = (uint32_t)(seq - seq0);
             const uint32_t t0 = s_tp[si], t1 = s_tp[si + 1];
             const uint32_t rd = s_rd[si * NQW + qw];
-            uint4 vnext = make_uint4(0, 0, 0, 0);
-            if (seq + 1 < seq_end) vnext = first_codes(si + 1);
             uint32_t r = t0 + qw;
             uint32_t cnt = rd & 0xFFFFu;
             const uint4 *src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3));
             // the bulk copy that last used this buffer must have read it: the previous part (one buffer) or the one
             // before it (two buffers, see `two`)
-            uint32_t *hist = csm + (two ? (si & 1u) * (S / 2) : 0u);
+            uint32_t *hist = csm + (two ? (si & 1u) * (p.hist_words / 2) : 0u);
             if (tid == 0) {
                 if (two) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 else bulk_wait_read();
             }
             __syncthreads();
-            for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) *reinterpret_cast<uint4 *>(hist + i) = make_uint4(0, 0, 0, 0);
+            if (!PROBE(2)) for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) *reinterpret_cast<uint4 *>(hist + i) = zero4;
             __syncthreads();
             // ---- count: one quarter-warp per run (sequences with more than NQW tiles take further rounds)
-            while (r < t1) {
-                for (uint32_t q = ql; 8u * q < cnt; q += 8) {
-                    if (q != ql) v = __ldg(src + q);
-                    const uint32_t left = cnt - 8u * q;
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int e8 = 0; e8 < 8; ++e8) {
-                        const uint32_t e = (e8 & 1) ? (w[e8 >> 1] >> 16) : (w[e8 >> 1] & 0xFFFFu);
-                        uint32_t col = e;
-                        if constexpr (CANON) {
-                            const uint32_t wd = (e >> 5) & (wps - 1u);   // (padding behind a run is arbitrary: stay inside the tables)
-                            col = s_pref[wd] + (uint32_t)__popc(s_bits[wd] & ~(0xFFFFFFFFu << (e & 31u)));
-                        }
-                        if ((uint32_t)e8 < left) atomicAdd(hist + col, 1u);
+            const bool extra = cnt > 128u || t1 - t0 > NQW;
+            if (r < t1) {
+                tally(v0, left_of(cnt, 8u * ql), 1u, hist);
+                tally(v1, left_of(cnt, 64u + 8u * ql), 1u, hist);
+            }
+            if (extra) {
+                while (r < t1) {
+                    for (uint32_t q = ql + 16; 8u * q < cnt; q += 8) tally(__ldg(src + q), cnt - 8u * q, 1u, hist);
+                    r += NQW;
+                    if (r < t1) {
+                        const uint32_t rd2 = __ldg(runs + r);
+                        cnt = rd2 & 0xFFFFu;
+                        src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd2 >> 16) << 3));
+                        for (uint32_t q = ql; 8u * q < cnt; q += 8) tally(__ldg(src + q), cnt - 8u * q, 1u, hist);
+                        cnt = 0;   // (this run is done)
                     }
                 }
-                r += NQW;
-                if (r < t1) {
-                    const uint32_t rd2 = __ldg(runs + r);
-                    cnt = rd2 & 0xFFFFu;
-                    src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd2 >> 16) << 3));
-                    if (8u * ql < cnt) v = __ldg(src + ql);
-                }
             }
-            v = vnext;
-            __syncthreads();
+            if (seq + 1 < seq_end) first_codes(si + 1, v0, v1);
             // ---- normalise and write this part of the row
-            const unsigned long long total = p.totals_in[seq];
+            const unsigned long long total = s_tot[si];
             if (tid == 0 && seg == 0 && p.totals_out) p.totals_out[seq] = total;
+            T *row = reinterpret_cast<T *>(p.out) + seq * p.dim + col0;
+            const bool bulk = OUT != OUT_F64 && (reinterpret_cast<uintptr_t>(row) & 15) == 0 && (bins & 3) == 0;
+            if constexpr (OUT == OUT_U32) {   // counts leave as they are: one barrier between the last atomic and the copy
+                fence_async_smem();
+                __syncthreads();
+                if (bulk) {
+                    if (tid == 0 && !PROBE(4)) bulk_store(row, hist, bins * 4u);
+                } else {
+                    for (uint32_t i = tid; i < bins; i += CK_THREADS) row[i] = hist[i];
+                }
+                continue;
+            }
+            __syncthreads();
             const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
             const float dF = (float)dv, rinv = __frcp_rn(dF);
             const double dD = (double)dv;
             const bool small = dv < (1ULL << 23);
-            T *row = reinterpret_cast<T *>(p.out) + seq * p.dim + col0;
             if constexpr (OUT == OUT_F64) {
                 for (uint32_t i = tid; i < bins; i += CK_THREADS) row[i] = cvt_count<OUT_F64, NORM, false>(hist[i], dF, rinv, dD);
             } else {
-                if ((reinterpret_cast<uintptr_t>(row) & 15) == 0 && (bins & 3) == 0) {
+                if (bulk) {
                     if constexpr (OUT == OUT_F32) {   // counts -> floats in place
                         for (uint32_t i = tid * 4u; i < bins; i += CK_THREADS * 4u) {
                             const uint4 c = *reinterpret_cast<const uint4 *>(hist + i);
@@ -423,7 +473,7 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
                     }
                     fence_async_smem();
                     __syncthreads();
-                    if (tid == 0) bulk_store(row, hist, bins * 4u);
+                    if (tid == 0 && !PROBE(4)) bulk_store(row, hist, bins * 4u);
                 } else {   // a part that does not start on a 16-byte boundary: plain coalesced stores
                     for (uint32_t i = tid; i < bins; i += CK_THREADS)
                         row[i] = small ? cvt_count<OUT, NORM, true>(hist[i], dF, rinv, dD) : cvt_count<OUT, NORM, false>(hist[i], dF, rinv, dD);

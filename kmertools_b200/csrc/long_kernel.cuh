@@ -108,8 +108,20 @@ __device__ __forceinline__ void k7_keys_phase(uint32_t cf, uint32_t cf_prev, uin
 
 // ---- write-out of one row into the row image (normalisation fused), histogram re-initialised on the way.
 // SMALL: every count and the divisor are below 2^23 (exact in f32, magic-constant conversion valid).
+// the first two schedule iterations of a warp (MODE_K7), requested before the barrier that precedes the write-out
+struct K7Sched {
+    uint4 A, B;
+    template <int NW>
+    __device__ __forceinline__ void load_nw(const uint32_t *sched, uint32_t warp, uint32_t lane) {
+        const uint4 *sched4 = reinterpret_cast<const uint4 *>(sched) + lane;
+        A = __ldg(sched4 + warp * 32);
+        B = (warp + NW < (K7_BINS >> 7)) ? __ldg(sched4 + (warp + NW) * 32) : make_uint4(0, 0, 0, 0);
+    }
+};
+
 template <int OUT, bool NORM, int MODE, int NW, bool SMALL, int RS>
-__device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hbytes, uint32_t *stage, uint64_t dv) {
+__device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hbytes, uint32_t *stage, uint64_t dv,
+                                               const K7Sched &ks) {
     using T = typename OutT<OUT>::type;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float dF = (float)dv;
@@ -156,8 +168,7 @@ __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hby
         };
         // the schedule comes from L2: two iterations in flight, registers A / B alternate (no copies between them)
         static_assert(niter % (2 * NW) == 0 || NW == 10, "iterations per warp");
-        uint4 A = __ldg(sched4 + warp * 32);
-        uint4 B = (warp + NW < niter) ? __ldg(sched4 + (warp + NW) * 32) : make_uint4(0, 0, 0, 0);
+        uint4 A = ks.A, B = ks.B;
         for (uint32_t w = warp; w < niter; w += 2 * NW) {
             const uint4 a = A;
             if (w + 2 * NW < niter) A = __ldg(sched4 + (w + 2 * NW) * 32);
@@ -206,7 +217,8 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
     static_assert(OUT == OUT_U32 || OUT == OUT_F32, "f64 rows keep seq_kernel");
     static_assert(NW == 4 || NW == 8 || NW == 10, "warps per CTA");
     extern __shared__ __align__(128) uint32_t lsm[];
-    __shared__ unsigned long long s_item;
+    __shared__ unsigned long long s_la[5];      // thread 0's look-ahead stream of work items
+    __shared__ __align__(8) unsigned long long s_nx[3][3];   // look-ahead work items (three slots): sequence or a marker, its two offsets
     __shared__ uint32_t s_total[2];
 
     uint32_t *hist = lsm;
@@ -237,105 +249,191 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
     const unsigned long long grab = p.grab ? p.grab : 1u;
     uint32_t it = 0;
 
-    for (;;) {
-        if (tid == 0) s_item = atomicAdd(p.counter, grab);
-        __syncthreads();
-        const unsigned long long item0 = s_item;
-        __syncthreads();
-        if (item0 >= nitems) break;
-        const unsigned long long item1 = min(item0 + grab, (unsigned long long)nitems);
-        for (unsigned long long item = item0; item < item1; ++item) {
-            const uint64_t gi = item >> gshift;
-            const uint64_t g = p.list ? (uint64_t)p.list[gi] : gi;
-            const uint64_t seq = (g << gshift) + (item - (gi << gshift));
-            if (seq >= p.n) continue;   // uniform for the CTA
-            const uint64_t s0 = p.offsets[seq];
-            const uint64_t s1 = p.offsets[seq + 1];
-            uint32_t mine = 0;
-            if (s1 - s0 >= k) {
-                const uint64_t cbase = s0 >> 4;
-                const uint32_t nch = (uint32_t)(((s1 - 1) >> 4) - cbase) + 1u;
-                // Contiguous runs of whole 32-chunk steps per warp.  A warp that starts inside the sequence loads, in lane 0 of
-                // its first step, the LAST chunk of the previous warp as look-back (that lane emits nothing), so no warp has
-                // to load and decode a priming chunk on its own: such a warp covers 32 * steps - 1 new chunks, and the step
-                // count carries NW - 1 chunks of slack.  Sequences of fewer steps than warps use the first warps only.
-                const uint32_t nsteps = (nch + (NW - 1) + 31) >> 5;
-                const uint32_t q0 = nsteps >= NW ? (warp * nsteps) / NW : min(warp, nsteps);
-                const uint32_t q1 = nsteps >= NW ? ((warp + 1) * nsteps) / NW : min(warp + 1, nsteps);
-                const bool lookback = q0 > 0;                                   // lane 0 of the first step re-reads chunk w0
-                const uint32_t w0 = lookback ? (q0 << 5) - warp : 0u;
-                const uint32_t w1 = min(nch, (q1 << 5) - warp);
-                const uint32_t head_mask = 0xFFFFu >> (uint32_t)(s0 & 15);
-                const uint32_t tail_mask = ~(0xFFFFu >> ((uint32_t)((s1 - 1) & 15) + 1u)) & 0xFFFFu;
-                if (q0 < q1 && w0 < w1) {
-                    uint32_t carry_cf = 0, carry_vm = 0;
-                    const uint4 *seq_chunks = reinterpret_cast<const uint4 *>(p.bases) + cbase;
-                    const bool near_end = ((cbase + nch) << 4) > p.total_bases;
-                    auto fetch = [&](uint32_t c) -> uint4 {
-                        if (c >= w1) return filler;
-                        if (near_end) return load16_guarded(p.bases, (cbase + c) << 4, p.total_bases);
-                        return __ldg(seq_chunks + c);
-                    };
-                    // two steps of bases in flight per warp (HBM latency is longer than one step of work at 24 warps/SM)
-                    // (two buffers used alternately, each reloaded right after it has been decoded: no register copies)
-                    uint4 buf_a = fetch(w0 + lane);
-                    uint4 buf_b = fetch(w0 + 32 + lane);
-                    auto do_step = [&](uint4 &buf, const uint32_t c0) {
-                        const uint32_t c = c0 + lane;
-                        uint32_t cf, vm;
-                        decode16(buf, cf, vm);
-                        if (c0 + 64 < w1) buf = fetch(c + 64);
-                        if (c >= w1) { vm = 0; cf = (uint32_t)lane * 0x9E3779B1u; }   // idle lanes add 0 at scattered bins
-                        if (c == 0) vm &= head_mask;
-                        if (c == nch - 1) vm &= tail_mask;
-                        uint32_t cf_prev = __shfl_up_sync(FULL, cf, 1);
-                        uint32_t vm_prev = __shfl_up_sync(FULL, vm, 1);
-                        if (lane == 0) { cf_prev = carry_cf; vm_prev = carry_vm; }
-                        carry_cf = __shfl_sync(FULL, cf, 31);
-                        carry_vm = __shfl_sync(FULL, vm, 31);
-                        uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
-                        const bool silent = lookback && c0 == w0 && lane == 0;   // the look-back lane of this warp's first step
-                        if (silent) vw = 0;
-                        mine += __popc(vw);
-                        uint32_t off[16];   // histogram byte offsets; off[e] = window ending at base e
-                        if constexpr (MODE == MODE_K7) {
-                            const uint32_t rc = revcomp_pack(cf), rc_prev = revcomp_pack(cf_prev);
-                            k7_keys_phase<0>(cf, cf_prev, rc, rc_prev, off);
-                            k7_keys_phase<1>(cf, cf_prev, rc, rc_prev, off);
-                            k7_keys_phase<2>(cf, cf_prev, rc, rc_prev, off);
-                            k7_keys_phase<3>(cf, cf_prev, rc, rc_prev, off);
-                        } else {
-                            const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
+    // ---- work items, two sequences ahead.  A sequence costs three dependent trips to memory before its first k-mer
+    // (work counter -> offsets -> bases); at one sequence per ~6 us and CTA that chain was a third of the time.  Thread 0
+    // runs a look-ahead stream of items: while sequence i is counted it draws the ticket of sequence i + 2, fetches its
+    // offsets during the write-out of i and publishes them in s_nx; every warp requests the first bases of sequence i + 1
+    // (known since the previous iteration) BEFORE the write-out of i.
+    constexpr unsigned long long ITEM_DONE = ~0ull, ITEM_SKIP = ~0ull - 1ull;
+    // (the stream's state lives in shared memory, touched by thread 0 only, and the offsets travel global -> shared with
+    // cp.async: nothing of the look-ahead occupies registers except the ticket that is in flight during the count loop)
+    unsigned long long tkt = 0;
+    bool want = false;
+    if (tid == 0) { s_la[0] = 0; s_la[1] = 0; s_la[2] = 0; s_la[3] = ~0ull; s_la[4] = 0; }
+    auto la_ticket = [&]() {
+        want = false;
+        if (tid == 0) {
+            const unsigned long long pos = s_la[0], end = s_la[1], dry = s_la[2];
+            want = !dry && pos == end;
+            if (want) tkt = atomicAdd(p.counter, grab);
+        }
+    };
+    auto la_resolve = [&](const uint32_t slot) {   // thread 0: next item of the stream -> s_nx[slot] (offsets asynchronously)
+        if (tid != 0) return;
+        // (the whole state is read at once: one shared-memory round trip on thread 0's path instead of a chain of them)
+        unsigned long long pos = s_la[0];
+        bool dry = s_la[2] != 0;
+        const unsigned long long last_gi = s_la[3], last_g = s_la[4];
+        if (want) {
+            pos = tkt;
+            dry = tkt >= nitems;
+            s_la[1] = min(tkt + grab, (unsigned long long)nitems);
+            if (dry) s_la[2] = 1;
+        }
+        unsigned long long nseq = ITEM_DONE;
+        if (!dry) {
+            s_la[0] = pos + 1;
+            const uint64_t gi = pos >> gshift;
+            uint64_t g = gi;
+            if (p.list) {   // one look-up per group of 2^gshift items
+                g = last_g;
+                if (last_gi != gi) { g = p.list[gi]; s_la[3] = gi; s_la[4] = g; }
+            }
+            const uint64_t seq = (g << gshift) + (pos - (gi << gshift));
+            nseq = seq < p.n ? seq : ITEM_SKIP;   // (padding of the last group)
+        }
+        s_nx[slot][0] = nseq;
+        if (nseq < ITEM_SKIP) {
+            const uint32_t dst = smem_u32addr(&s_nx[slot][1]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(p.offsets + nseq) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst + 8u), "l"(p.offsets + nseq + 1) : "memory");
+        } else {
+            s_nx[slot][1] = 0; s_nx[slot][2] = 0;
+        }
+    };
+    auto la_arrived = [&]() {   // before the barrier that publishes the slot
+        if (tid == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+    };
+
+    // what a warp does with a sequence: contiguous runs of whole 32-chunk steps per warp.  A warp that starts inside the
+    // sequence loads, in lane 0 of its first step, the LAST chunk of the previous warp as look-back (that lane emits
+    // nothing), so no warp has to load and decode a priming chunk on its own: such a warp covers 32 * steps - 1 new
+    // chunks, and the step count carries NW - 1 chunks of slack.  Sequences of fewer steps than warps use the first warps.
+    struct Plan { uint64_t cbase; uint32_t nch, w0, w1, flags; };   // flags: 1 = look-back lane, 2 = guarded loads
+    auto make_plan = [&](const uint64_t s0, const uint64_t s1) -> Plan {
+        Plan pl{0, 0, 0, 0, 0};
+        if (s1 - s0 >= k) {
+            pl.cbase = s0 >> 4;
+            pl.nch = (uint32_t)(((s1 - 1) >> 4) - pl.cbase) + 1u;
+            const uint32_t nsteps = (pl.nch + (NW - 1) + 31) >> 5;
+            const uint32_t q0 = nsteps >= NW ? (warp * nsteps) / NW : min(warp, nsteps);
+            const uint32_t q1 = nsteps >= NW ? ((warp + 1) * nsteps) / NW : min(warp + 1, nsteps);
+            const uint32_t w0 = q0 > 0 ? (q0 << 5) - warp : 0u;   // lane 0 of the first step re-reads chunk w0
+            const uint32_t w1 = min(pl.nch, (q1 << 5) - warp);
+            if (q0 < q1 && w0 < w1) {
+                pl.w0 = w0; pl.w1 = w1;
+                pl.flags = (q0 > 0 ? 1u : 0u) | ((((pl.cbase + pl.nch) << 4) > p.total_bases) ? 2u : 0u);
+            }
+        }
+        return pl;
+    };
+    auto fetch = [&](const Plan &pl, const uint32_t c) -> uint4 {
+        if (c >= pl.w1) return filler;
+        if (pl.flags & 2u) return load16_guarded(p.bases, (pl.cbase + c) << 4, p.total_bases);
+        return __ldg(reinterpret_cast<const uint4 *>(p.bases) + pl.cbase + c);
+    };
+
+    // Only k = 7 looks ahead.  The small histograms of k <= 5 run 4 - 8 CTAs per SM, which hide those latencies already
+    // (measured with look-ahead: -3 % on 10 kbp reads at k = 5), and a CTA that reserves two 500 kbp contigs in advance
+    // lengthens the tail of the launch (-5 % on config 4).
+    constexpr bool LA = (MODE == MODE_K7);
+    // prologue: the first two items, with their latencies exposed once per CTA
+    la_ticket(); la_resolve(0);
+    if constexpr (LA) { la_ticket(); la_resolve(1); }
+    la_arrived();
+    __syncthreads();
+    unsigned long long seq = s_nx[0][0];
+    uint32_t head_mask, tail_mask;
+    Plan pl;
+    {
+        const unsigned long long s0 = s_nx[0][1], s1 = s_nx[0][2];
+        head_mask = 0xFFFFu >> (uint32_t)(s0 & 15);
+        tail_mask = ~(0xFFFFu >> ((uint32_t)((s1 - 1) & 15) + 1u)) & 0xFFFFu;
+        pl = make_plan(s0, s1);
+    }
+    __syncthreads();
+    // three slots in rotation: the NEXT item's record (read in this iteration), the one thread 0 is filling, and the one the
+    // current item came from (still being read by slower warps when thread 0 starts to fill)
+    uint32_t slot = 1;
+    // two steps of bases in flight per warp (two buffers used alternately, each reloaded right after it has been decoded)
+    uint4 buf_a = fetch(pl, pl.w0 + lane);
+    uint4 buf_b = fetch(pl, pl.w0 + 32 + lane);
+
+    while (seq != ITEM_DONE) {
+        if constexpr (LA) la_ticket();
+        const bool real = seq != ITEM_SKIP;   // uniform for the CTA
+        uint32_t mine = 0;
+        if (pl.w0 < pl.w1) {
+            const uint32_t nch = pl.nch, w0 = pl.w0, w1 = pl.w1;
+            const bool lookback = pl.flags & 1u;
+            uint32_t carry_cf = 0, carry_vm = 0;
+            auto do_step = [&](uint4 &buf, const uint32_t c0) {
+                const uint32_t c = c0 + lane;
+                uint32_t cf, vm;
+                decode16(buf, cf, vm);
+                if (c0 + 64 < w1) buf = fetch(pl, c + 64);
+                if (c >= w1) { vm = 0; cf = (uint32_t)lane * 0x9E3779B1u; }   // idle lanes add 0 at scattered bins
+                if (c == 0) vm &= head_mask;
+                if (c == nch - 1) vm &= tail_mask;
+                uint32_t cf_prev = __shfl_up_sync(FULL, cf, 1);
+                uint32_t vm_prev = __shfl_up_sync(FULL, vm, 1);
+                if (lane == 0) { cf_prev = carry_cf; vm_prev = carry_vm; }
+                carry_cf = __shfl_sync(FULL, cf, 31);
+                carry_vm = __shfl_sync(FULL, vm, 31);
+                uint32_t vw = window_mask((vm_prev << 16) | vm, k) & 0xFFFFu;
+                const bool silent = lookback && c0 == w0 && lane == 0;   // the look-back lane of this warp's first step
+                if (silent) vw = 0;
+                mine += __popc(vw);
+                uint32_t off[16];   // histogram byte offsets; off[e] = window ending at base e
+                if constexpr (MODE == MODE_K7) {
+                    const uint32_t rc = revcomp_pack(cf), rc_prev = revcomp_pack(cf_prev);
+                    k7_keys_phase<0>(cf, cf_prev, rc, rc_prev, off);
+                    k7_keys_phase<1>(cf, cf_prev, rc, rc_prev, off);
+                    k7_keys_phase<2>(cf, cf_prev, rc, rc_prev, off);
+                    k7_keys_phase<3>(cf, cf_prev, rc, rc_prev, off);
+                } else {
+                    const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) {
-                                constexpr int up = 2 + RS;                       // window e sits at bit 2 (15 - e) of F64
-                                const int sh = 2 * (15 - e) - up;
-                                const uint32_t x = sh >= 0 ? (uint32_t)(F64 >> (sh >= 0 ? sh : 0)) : (cf << (sh < 0 ? -sh : 0));
-                                off[e] = (x & kmaskR) | lane_off;
-                            }
-                        }
-                        if (__all_sync(FULL, vw == 0xFFFFu)) {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), 1u);
-                        } else if (__all_sync(FULL, silent || vw == 0xFFFFu)) {   // full step behind a look-back lane
-                            const uint32_t inc = silent ? 0u : 1u;
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), inc);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e)   // branch-free: an invalid window adds 0
-                                atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), (vw >> (15 - e)) & 1u);
-                        }
-                    };
-                    for (uint32_t c0 = w0; c0 < w1; c0 += 64) {
-                        do_step(buf_a, c0);
-                        if (c0 + 32 < w1) do_step(buf_b, c0 + 32);
+                    for (int e = 0; e < 16; ++e) {
+                        constexpr int up = 2 + RS;                       // window e sits at bit 2 (15 - e) of F64
+                        const int sh = 2 * (15 - e) - up;
+                        const uint32_t x = sh >= 0 ? (uint32_t)(F64 >> (sh >= 0 ? sh : 0)) : (cf << (sh < 0 ? -sh : 0));
+                        off[e] = (x & kmaskR) | lane_off;
                     }
                 }
+                if (__all_sync(FULL, vw == 0xFFFFu)) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), 1u);
+                } else if (__all_sync(FULL, silent || vw == 0xFFFFu)) {   // full step behind a look-back lane
+                    const uint32_t inc = silent ? 0u : 1u;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), inc);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)   // branch-free: an invalid window adds 0
+                        atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), (vw >> (15 - e)) & 1u);
+                }
+            };
+            for (uint32_t c0 = w0; c0 < w1; c0 += 64) {
+                do_step(buf_a, c0);
+                if (c0 + 32 < w1) do_step(buf_b, c0 + 32);
             }
+        }
+        // the next sequence's first bases travel during the write-out of this one (its plan is worked out again afterwards:
+        // cheaper than eight more live registers across the write-out)
+        const uint32_t slot_w = slot == 2u ? 0u : slot + 1u;
+        if constexpr (LA) {
+            const Plan pl_n = make_plan(s_nx[slot][1], s_nx[slot][2]);
+            buf_a = fetch(pl_n, pl_n.w0 + lane);
+            buf_b = fetch(pl_n, pl_n.w0 + 32 + lane);
+            la_resolve(slot_w);   // the item after that: its offsets travel during the write-out, too
+        }
+        if (real) {
             // ---- total = block sum of `mine`
             mine = __reduce_add_sync(FULL, mine);
             if (lane == 0 && mine) atomicAdd(&s_total[it & 1], mine);
+            K7Sched ks;
+            if constexpr (MODE == MODE_K7) ks.template load_nw<NW>(p.sched, warp, lane);
             // the row image is about to be overwritten: the bulk copy of the previous row must have read it
             if (tid == 0) bulk_wait_read();
             __syncthreads();
@@ -344,11 +442,25 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
             ++it;
             const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
             if (tid == 0 && p.totals) p.totals[seq] = total;
-            if (dv < (1ULL << 23)) long_write_row<OUT, NORM, MODE, NW, true, RS>(p, hbytes, stage, dv);
-            else long_write_row<OUT, NORM, MODE, NW, false, RS>(p, hbytes, stage, dv);
+            if (dv < (1ULL << 23)) long_write_row<OUT, NORM, MODE, NW, true, RS>(p, hbytes, stage, dv, ks);
+            else long_write_row<OUT, NORM, MODE, NW, false, RS>(p, hbytes, stage, dv, ks);
             fence_async_smem();
-            __syncthreads();
-            if (tid == 0) bulk_store(out + seq * (uint64_t)p.dim, stage, p.dim * 4u);
+        }
+        if constexpr (!LA) { la_ticket(); la_resolve(slot); }   // (slot 1 <-> 2: not the one the current item was read from)
+        la_arrived();
+        __syncthreads();
+        if (real && tid == 0) bulk_store(out + seq * (uint64_t)p.dim, stage, p.dim * 4u);
+        seq = s_nx[slot][0];
+        {
+            const unsigned long long s0 = s_nx[slot][1], s1 = s_nx[slot][2];
+            head_mask = 0xFFFFu >> (uint32_t)(s0 & 15);
+            tail_mask = ~(0xFFFFu >> ((uint32_t)((s1 - 1) & 15) + 1u)) & 0xFFFFu;
+            pl = make_plan(s0, s1);
+        }
+        slot = slot_w;
+        if constexpr (!LA) {
+            buf_a = fetch(pl, pl.w0 + lane);
+            buf_b = fetch(pl, pl.w0 + 32 + lane);
         }
     }
     if (tid == 0) bulk_wait_all();
