@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
     __shared__ unsigned long long s_unit;
     __shared__ uint32_t s_tp[CK_SEQ_CHUNK + 1];   // tile prefix of the chunk's sequences
     __shared__ unsigned long long s_tot[CK_SEQ_CHUNK];   // valid windows of the chunk's sequences
+    __shared__ uint32_t s_trash[32];
     __shared__ uint32_t s_rd[CK_THREADS];         // descriptor of every quarter-warp's first run, per sequence of the chunk
     static_assert(CK_THREADS == CK_SEQ_CHUNK * (CK_THREADS / 8), "one descriptor slot per (sequence, quarter-warp)");
     using T = typename OutT<OUT>::type;
@@ -316,6 +317,12 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
     constexpr uint32_t NQW = CK_THREADS / 8;
     const uint32_t ntiles = p.tile_prefix[p.n];
     const uint64_t nunits = (p.chunk_hi - p.chunk_lo) * p.nseg;
+    // Kept in registers on purpose: re-reading a kernel parameter from the constant bank at the top of the sequence loop
+    // (LDC) took the scoreboard of the code loads that are in flight across iterations and waited for them — 18 % of the
+    // kernel's stall samples (profiles/r2_ncu_count_summary.txt) — which undid the prefetch.
+    // (threadIdx.y is 0, which the assembler cannot know: the sums are values it has to keep, not parameters it can re-read)
+    const uint16_t *pool = p.pool + threadIdx.y;
+    const uint32_t hist_half = p.hist_words / 2 + threadIdx.y;
     // units differ in cost (segments hold between none and twice the average number of k-mers), so they are dealt out
     // dynamically; the counter is read one unit ahead to keep its round trip off the critical path
     unsigned long long next_unit = 0;
@@ -372,12 +379,14 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
         auto first_codes = [&](const uint32_t i, uint4 &a, uint4 &b) {
             const uint32_t rdi = s_rd[i * NQW + qw];
             const uint32_t c = rdi & 0xFFFFu;
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)(s_tp[i] + qw) * BK_TILE_CAP + ((uint64_t)(rdi >> 16) << 3));
+            const uint4 *src = reinterpret_cast<const uint4 *>(pool + (uint64_t)(s_tp[i] + qw) * BK_TILE_CAP + ((uint64_t)(rdi >> 16) << 3));
             a = (8u * ql < c && !PROBE(8)) ? __ldg(src + ql) : zero4;
             b = (64u + 8u * ql < c && !PROBE(8)) ? __ldg(src + 8 + ql) : zero4;
         };
         // add `delta` to the bins of the first `left` of the eight codes in v
-        auto tally = [&](const uint4 v, const uint32_t left, const uint32_t delta, uint32_t *hist) {
+        // (branch-free inside: the codes behind the end of a run add 1 to a trash word of their own lane)
+        auto tally = [&](const uint4 v, const uint32_t left, uint32_t *hist) {
+            if (left == 0 || PROBE(1)) return;
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e8 = 0; e8 < 8; ++e8) {
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
                     const uint32_t wd = (e >> 5) & (wps - 1u);   // (padding behind a run is arbitrary: stay inside the tables)
                     col = s_pref[wd] + (uint32_t)__popc(s_bits[wd] & ~(0xFFFFFFFFu << (e & 31u)));
                 }
-                if ((uint32_t)e8 < left && !PROBE(1)) atomicAdd(hist + col, delta);
+                atomicAdd((uint32_t)e8 < left ? hist + col : s_trash + (tid & 31), 1u);
             }
         };
         auto left_of = [&](const uint32_t cnt, const uint32_t first) -> uint32_t { return cnt > first ? cnt - first : 0u; };
@@ -402,10 +411,9 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
             const uint32_t rd = s_rd[si * NQW + qw];
             uint32_t r = t0 + qw;
             uint32_t cnt = rd & 0xFFFFu;
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3));
             // the bulk copy that last used this buffer must have read it: the previous part (one buffer) or the one
             // before it (two buffers, see `two`)
-            uint32_t *hist = csm + (two ? (si & 1u) * (p.hist_words / 2) : 0u);
+            uint32_t *hist = csm + (two ? (si & 1u) * hist_half : 0u);
             if (tid == 0) {
                 if (two) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 else bulk_wait_read();
@@ -416,18 +424,19 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
             // ---- count: one quarter-warp per run (sequences with more than NQW tiles take further rounds)
             const bool extra = cnt > 128u || t1 - t0 > NQW;
             if (r < t1) {
-                tally(v0, left_of(cnt, 8u * ql), 1u, hist);
-                tally(v1, left_of(cnt, 64u + 8u * ql), 1u, hist);
+                tally(v0, left_of(cnt, 8u * ql), hist);
+                tally(v1, left_of(cnt, 64u + 8u * ql), hist);
             }
             if (extra) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd >> 16) << 3));
                 while (r < t1) {
-                    for (uint32_t q = ql + 16; 8u * q < cnt; q += 8) tally(__ldg(src + q), cnt - 8u * q, 1u, hist);
+                    for (uint32_t q = ql + 16; 8u * q < cnt; q += 8) tally(__ldg(src + q), cnt - 8u * q, hist);
                     r += NQW;
                     if (r < t1) {
                         const uint32_t rd2 = __ldg(runs + r);
                         cnt = rd2 & 0xFFFFu;
-                        src = reinterpret_cast<const uint4 *>(p.pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd2 >> 16) << 3));
-                        for (uint32_t q = ql; 8u * q < cnt; q += 8) tally(__ldg(src + q), cnt - 8u * q, 1u, hist);
+                        src = reinterpret_cast<const uint4 *>(pool + (uint64_t)r * BK_TILE_CAP + ((uint64_t)(rd2 >> 16) << 3));
+                        for (uint32_t q = ql; 8u * q < cnt; q += 8) tally(__ldg(src + q), cnt - 8u * q, hist);
                         cnt = 0;   // (this run is done)
                     }
                 }
