@@ -328,8 +328,9 @@ int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
         // set-up of 8 warps); 8 warps for long contigs
         // measured (profiles/r2_sweeps.txt): k = 7 rows ran best with 10 warps per CTA (three CTAs per SM of 64 KB each)
         // until the kernel looked ahead across sequences; that needs 72 registers, which 8 warps have and 10 do not
-        // (799 against 765 Gbases/s on config 3).  The small histograms of k <= 5 run best with 4 warps
-        int nw = h->long_warps > 0 ? h->long_warps : (mode == MODE_K7 ? (mean_len < 1024 ? 10 : 8) : (mean_len <= 32768 ? 4 : 8));
+        // (799 against 765 Gbases/s on config 3, 20.6 against 18.6 on 150-base reads).  The small histograms of k <= 5 run
+        // best with 4 warps
+        int nw = h->long_warps > 0 ? h->long_warps : (mode == MODE_K7 ? 8 : (mean_len <= 32768 ? 4 : 8));
         if (nw == 10 && mode != MODE_K7) nw = 8;
         void (*kern)(const LongParams) = nullptr;
         int rs = 0;

@@ -188,13 +188,13 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const uint32_t sg = lane_ok ? (cp[j] >> p.log2_seg) : trash;
-                cp[j] |= atomicAdd(&s_cnt[sg], 1u) << 20;
+                cp[j] += atomicAdd(&s_cnt[sg], 1u) << 20;   // (+: one shift-add; the fields do not overlap)
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const uint32_t sg = (vw & (1u << (15 - j))) ? (cp[j] >> p.log2_seg) : trash;
-                cp[j] |= atomicAdd(&s_cnt[sg], 1u) << 20;
+                cp[j] += atomicAdd(&s_cnt[sg], 1u) << 20;   // (+: one shift-add; the fields do not overlap)
             }
         }
         if (more) v = load_chunk(nti);   // the next tile's bases are on their way while this tile is sorted

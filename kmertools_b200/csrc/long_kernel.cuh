@@ -168,15 +168,15 @@ __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hby
         };
         // the schedule comes from L2: two iterations in flight, registers A / B alternate (no copies between them)
         static_assert(niter % (2 * NW) == 0 || NW == 10, "iterations per warp");
+        // (each register set is reloaded right after the iteration that consumed it: no copies, and the load has the other
+        // set's iteration — ~500 clocks at 24 warps per SM — to come back from L2)
         uint4 A = ks.A, B = ks.B;
         for (uint32_t w = warp; w < niter; w += 2 * NW) {
-            const uint4 a = A;
+            move4(A);
             if (w + 2 * NW < niter) A = __ldg(sched4 + (w + 2 * NW) * 32);
-            move4(a);
             if (w + NW < niter) {
-                const uint4 b = B;
+                move4(B);
                 if (w + 3 * NW < niter) B = __ldg(sched4 + (w + 3 * NW) * 32);
-                move4(b);
             }
         }
     } else if constexpr (RS == 0) {
