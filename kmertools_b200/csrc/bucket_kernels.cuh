@@ -290,7 +290,10 @@ struct CountParams {
 #define PROBE(bit) false
 #endif
 
-constexpr int CK_SEQ_CHUNK = 8;   // consecutive sequences that share one load of a segment's rank tables
+#ifndef KTB_CK_SEQ_CHUNK
+#define KTB_CK_SEQ_CHUNK 8
+#endif
+constexpr int CK_SEQ_CHUNK = KTB_CK_SEQ_CHUNK;   // consecutive sequences per work unit (multiple of 8)
 
 // One CTA per (segment of the code space, chunk of CK_SEQ_CHUNK sequences).  The columns of the segment are
 // [R, R + bins): R = rank of the segment's first code.  For every sequence of the chunk the runs of the segment (one
@@ -305,8 +308,8 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
     __shared__ uint32_t s_tp[CK_SEQ_CHUNK + 1];   // tile prefix of the chunk's sequences
     __shared__ unsigned long long s_tot[CK_SEQ_CHUNK];   // valid windows of the chunk's sequences
     __shared__ uint32_t s_trash[32];
-    __shared__ uint32_t s_rd[CK_THREADS];         // descriptor of every quarter-warp's first run, per sequence of the chunk
-    static_assert(CK_THREADS == CK_SEQ_CHUNK * (CK_THREADS / 8), "one descriptor slot per (sequence, quarter-warp)");
+    __shared__ uint32_t s_rd[CK_SEQ_CHUNK * (CK_THREADS / 8)];   // descriptor of every quarter-warp's first run, per sequence of the chunk
+    static_assert(CK_SEQ_CHUNK % 8 == 0 && CK_THREADS == 256, "descriptor staging: 8 sequences x 32 quarter-warps per pass");
     using T = typename OutT<OUT>::type;
     const uint32_t S = 1u << p.log2_seg;                 // codes per segment
     const uint32_t wps = S / 32;                         // bitmap words per segment
@@ -327,6 +330,8 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
     // dynamically; the counter is read one unit ahead to keep its round trip off the critical path
     unsigned long long next_unit = 0;
     if (tid == 0) next_unit = atomicAdd(p.counter, 1ULL);
+    uint32_t cur_seg = 0xFFFFFFFFu;   // the segment whose tables are in shared memory
+    uint64_t col0 = 0, col1 = 0;      // its columns
     for (;;) {
         __syncthreads();      // everyone is done with s_unit and the tables of the previous unit
         if (tid == 0) {
@@ -336,23 +341,29 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
         __syncthreads();
         const unsigned long long unit = s_unit;
         if (unit >= nunits) break;
+        // units are numbered chunk-major (consecutive units = the segments of one chunk of sequences), so CTAs that run side
+        // by side work on segments of every size.  Measured against segment-major order (large segments first, tables kept
+        // while a CTA stays in a segment; profiles/r2_sweeps.txt, batch r2v): 1.32 against 1.36 ms for u32 rows on config
+        // 5ii, 1.50 against 1.49 ms for f32 rows.
         const uint64_t chunk = p.chunk_lo + unit / p.nseg;
         const uint32_t seg = (uint32_t)(unit % p.nseg);
-        uint64_t col0, col1;   // columns of this segment
         if constexpr (CANON) {
-            const uint32_t *gpref = p.rank_tab + p.tab_words;
-            col0 = gpref[(size_t)seg * (wps / 2)];
-            col1 = (seg + 1 < p.nseg) ? (uint64_t)gpref[(size_t)(seg + 1) * (wps / 2)] : p.dim;
-            for (uint32_t w = tid; w < wps; w += CK_THREADS) {
-                const uint32_t bits = __ldg(p.rank_tab + (size_t)seg * wps + w);
-                const uint32_t prev = (w & 1u) ? __ldg(p.rank_tab + (size_t)seg * wps + w - 1) : 0u;
-                s_bits[w] = bits;
-                s_pref[w] = __ldg(gpref + ((size_t)seg * wps + w) / 2) - (uint32_t)col0 + (uint32_t)__popc(prev);
+            if (seg != cur_seg) {
+                const uint32_t *gpref = p.rank_tab + p.tab_words;
+                col0 = gpref[(size_t)seg * (wps / 2)];
+                col1 = (seg + 1 < p.nseg) ? (uint64_t)gpref[(size_t)(seg + 1) * (wps / 2)] : p.dim;
+                for (uint32_t w = tid; w < wps; w += CK_THREADS) {
+                    const uint32_t bits = __ldg(p.rank_tab + (size_t)seg * wps + w);
+                    const uint32_t prev = (w & 1u) ? __ldg(p.rank_tab + (size_t)seg * wps + w - 1) : 0u;
+                    s_bits[w] = bits;
+                    s_pref[w] = __ldg(gpref + ((size_t)seg * wps + w) / 2) - (uint32_t)col0 + (uint32_t)__popc(prev);
+                }
             }
         } else {
             col0 = (uint64_t)seg * S;
             col1 = min(p.dim, col0 + S);
         }
+        cur_seg = seg;
         const uint32_t bins = (uint32_t)(col1 - col0);   // multiple of 4 for every k this path serves (checked on the host)
         if (bins == 0) continue;                         // uniform: a segment without canonical codes
         const uint32_t *runs = p.runs + (uint64_t)seg * ntiles;
@@ -364,12 +375,13 @@ __global__ void __launch_bounds__(CK_THREADS, 3) count_kernel(const CountParams 
         // alternate between the two halves of the histogram memory, so the CTA never waits for its own last bulk copy
         const bool two = bins * 2u <= p.hist_words;
         if (tid == 0) bulk_wait_read();   // buffers change roles between units
-        {
-            const uint32_t j = tid >> 5, q = tid & 31;   // CK_THREADS = CK_SEQ_CHUNK * NQW
+#pragma unroll
+        for (uint32_t j0 = 0; j0 < (uint32_t)CK_SEQ_CHUNK; j0 += 8) {
+            const uint32_t j = j0 + (tid >> 5), q = tid & 31;   // 8 sequences x NQW quarter-warps per pass
             const uint32_t a0 = p.tile_prefix[min(p.n, seq0 + j)], a1 = p.tile_prefix[min(p.n, seq0 + j + 1)];
-            s_rd[tid] = (a0 + q < a1) ? __ldg(runs + a0 + q) : 0u;
+            s_rd[j * NQW + q] = (a0 + q < a1) ? __ldg(runs + a0 + q) : 0u;
             if (q == 0) s_tp[j] = a0;
-            if (tid == CK_THREADS - 1) s_tp[CK_SEQ_CHUNK] = a1;
+            if (q == 2 && j == (uint32_t)CK_SEQ_CHUNK - 1) s_tp[CK_SEQ_CHUNK] = a1;
             if (q == 1) s_tot[j] = p.totals_in[min(p.n - 1, seq0 + j)];   // (a load per sequence here would stall every thread)
         }
         __syncthreads();

@@ -1,0 +1,29 @@
+#!/bin/bash
+# round-2 GPU batch V: A/B/C on one box — A = previous commit, B = count_kernel units segment-major with table reuse,
+# C = B with 16 sequences per unit
+mkdir -p gpurun_out
+O=gpurun_out/r2v
+cp kmertools_b200/lib/libkmertools_b200.so /tmp/libB.so
+timeout 900 python -m pytest tests/test_gpu_bucket.py -m gpu -x -q > $O.pytest.txt 2>&1; echo "rc=$?" >> $O.pytest.txt
+tail -3 $O.pytest.txt
+cp tools/_probe/libC.so kmertools_b200/lib/libkmertools_b200.so
+timeout 900 python -m pytest tests/test_gpu_bucket.py -m gpu -x -q > $O.pytestC.txt 2>&1; echo "rc=$?" >> $O.pytestC.txt
+tail -3 $O.pytestC.txt
+run() { # tag workload scale opts...
+  tag=$1; w=$2; sc=$3; shift 3; flags=""; for kv in "$@"; do flags="$flags --opt $kv"; done
+  timeout 300 python bench.py --workload $w --scale $sc --steps 8 --no-e2e --no-cpu --no-cli --no-per-config $flags 2>&1 | tail -1 | \
+    python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$tag', '$w', '$sc', '$*', 'Gb/s', round(d['value'],1), 'ms', round(d['ms_per_step'],3), 'frac', round(d['roofline']['frac'],3), 'rows1', d['rows_sum_to_one'])"
+}
+{
+for rep in 1 2; do
+  for L in A B C; do
+    if [ $L = A ]; then cp tools/_probe/libA.so kmertools_b200/lib/libkmertools_b200.so; fi
+    if [ $L = B ]; then cp /tmp/libB.so kmertools_b200/lib/libkmertools_b200.so; fi
+    if [ $L = C ]; then cp tools/_probe/libC.so kmertools_b200/lib/libkmertools_b200.so; fi
+    run $L reads100k_k10 1.0
+    run $L reads100k_k10_f32 1.0
+    run $L reads100k_k9 0.5
+  done
+done
+} > $O.sweep.txt 2>&1
+cat $O.sweep.txt
