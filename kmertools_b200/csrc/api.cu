@@ -139,6 +139,7 @@ struct ktb_oligo {
     int64_t fwd_min_len = 1024;   // mean sequence length from which MODE_FWD replaces seq_kernel mode 1
     int bucket = 1;       // rows larger than shared memory: bucket_kernel + count_kernel instead of global atomics
     int bucket_hist_kb = 64;    // histogram memory of count_kernel per CTA: 64 KB (three CTAs per SM) or 96 KB (two)
+    int bucket_wave_ctas = 2;   // bucket_kernel CTAs per SM when the path runs in waves (beside count_kernel's three)
     int bucket_waves = 1;       // waves of that path (bucket_kernel of wave w+1 overlaps count_kernel of wave w); measured: 1 is best
     int bucket_log2_seg = 14;   // columns per segment of that path (2^14 u32 bins = 64 KB of shared memory)
     int packed16 = 1;     // seq_kernel mode 5 (k = 8: packed 16-bit rank-space histogram, 2 CTAs/SM)
@@ -548,7 +549,7 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
             CU(cudaStreamWaitEvent(sb, h->aux_ev[2], 0));
             CU(cudaStreamWaitEvent(sc, h->aux_ev[2], 0));
         }
-        const int b_ctas = nwaves > 1 ? std::min(b_per_sm, 2) : b_per_sm;
+        const int b_ctas = nwaves > 1 ? std::min(b_per_sm, h->bucket_wave_ctas) : b_per_sm;
         for (uint64_t w = 0; w < nwaves; ++w) {
             const uint64_t c_lo = nchunks * w / nwaves, c_hi = nchunks * (w + 1) / nwaves;
             bp.seq_lo = std::min(n, c_lo * CK_SEQ_CHUNK); bp.seq_hi = std::min(n, c_hi * CK_SEQ_CHUNK);
@@ -1047,6 +1048,9 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
     } else if (!strcmp(key, "bucket_hist_kb")) {
         if (value != 64 && value != 96) return fail(KTB_ERR_ARG, "bucket_hist_kb must be 64 or 96");
         h->bucket_hist_kb = (int)value;
+    } else if (!strcmp(key, "bucket_wave_ctas")) {
+        if (value < 1 || value > 4) return fail(KTB_ERR_ARG, "bucket_wave_ctas must be in 1..4");
+        h->bucket_wave_ctas = (int)value;
     } else if (!strcmp(key, "bucket_waves")) {
         if (value < 1 || value > 64) return fail(KTB_ERR_ARG, "bucket_waves must be in 1..64");
         h->bucket_waves = (int)value;

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) tile_info_kernel(const uint64_t *offsets,
 
 template <bool CANON>
 __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketParams p) {
-    __shared__ __align__(128) uint16_t stage[BK_TILE_CAP + 32];   // sorted tile; the last 32 entries swallow invalid windows
+    __shared__ __align__(128) uint16_t stage[BK_TILE_CAP + BK_WARPS * 32];   // sorted tile; behind it one entry per thread that swallows its invalid windows
     __shared__ uint32_t s_cnt[BK_MAX_SEG + 1];  // codes of this tile per segment; [nseg] collects the invalid windows
     __shared__ uint32_t s_base[BK_MAX_SEG + 1]; // first staging entry of the segment's run (multiple of 8); [nseg] = trash
     __shared__ uint32_t s_tot;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
         // ---- phase 3: scatter the in-segment codes to their runs (branch-free: invalid windows land in the trash
         // entries), then one bulk copy of the sorted tile into its pool slot
         // (an invalid window reads the base of whatever segment its stale code names — harmless — and is redirected)
-        const uint32_t trash_slot = BK_TILE_CAP + lane;
+        const uint32_t trash_slot = BK_TILE_CAP + tid;   // (per thread: no two threads ever store to the same entry)
         if (steady) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {

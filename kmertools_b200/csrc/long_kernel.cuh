@@ -180,13 +180,14 @@ __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hby
             }
         }
     } else if constexpr (RS == 0) {
+        const uint32_t zero_off = (p.hist_words - 4u) << 2;   // byte offset of the word at 4^k
         for (uint32_t j = tid; j < p.dim; j += NW * 32) {
             const uint32_t e = __ldg(p.sched + j);
             uint32_t *a = reinterpret_cast<uint32_t *>(hbytes + (e & 0xFFFFu));
             uint32_t *b = reinterpret_cast<uint32_t *>(hbytes + (e >> 16));
             const uint32_t cnt = *a + *b;   // palindromes: b is the always-zero word
             *a = 0;
-            *b = 0;
+            if ((e >> 16) != zero_off) *b = 0;   // (the zero word is shared by every palindrome: never stored to)
             reinterpret_cast<T *>(stage)[j] = cvt_count<OUT, NORM, SMALL>(cnt, dF, rinv, dD);
         }
     } else {
