@@ -520,6 +520,10 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
         if (const char *e = getenv("KTB_COUNT_PROBE")) cp.probe = (uint32_t)atoi(e);
 #endif
         void (*bkern)(const BucketParams) = canonical ? bucket_kernel<true> : bucket_kernel<false>;
+        if (canonical && log2_seg == 14) {   // the two shapes BASELINE.json names get their constants at compile time
+            if (h->k == 10) bkern = bucket_kernel<true, 10, 14>;
+            else if (h->k == 9) bkern = bucket_kernel<true, 9, 14>;
+        }
         const bool nrm = norm_mode != NORM_COUNTS;
         void (*ckern)(const CountParams) =
             canonical ? (nrm ? count_kernel<OUT, true, true> : count_kernel<OUT, false, true>)

@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) tile_info_kernel(const uint64_t *offsets,
     }
 }
 
-template <bool CANON>
+// KT, LS: compile-time k and log2 of the segment size (0 = from the parameters)
+template <bool CANON, int KT = 0, int LS = 0>
 __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketParams p) {
     __shared__ __align__(128) uint16_t stage[BK_TILE_CAP + BK_WARPS * 32];   // sorted tile; behind it one entry per thread that swallows its invalid windows
     __shared__ uint32_t s_cnt[BK_MAX_SEG + 1];  // codes of this tile per segment; [nseg] collects the invalid windows
@@ -120,9 +121,10 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t warp = tid >> 5;
     constexpr uint32_t FULL = 0xffffffffu;
-    const uint32_t k = p.k;
+    const uint32_t k = KT ? (uint32_t)KT : p.k;
+    const uint32_t log2_seg = LS ? (uint32_t)LS : p.log2_seg;
     const uint32_t kmask = (1u << (2 * k)) - 1u;
-    const uint32_t seg_mask = (1u << p.log2_seg) - 1u;
+    const uint32_t seg_mask = (1u << log2_seg) - 1u;
     const uint32_t trash = p.nseg;
     const uint64_t ntiles = p.tile_prefix[p.n];
     const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
@@ -170,7 +172,9 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
         // reverse strand, shifted once so that window j sits at bit 2j: base i of R64 is at bit 2(i + 16)
         uint32_t rlo = 0, rhi = 0;
         if constexpr (CANON) {
-            const uint64_t R64 = (((uint64_t)revcomp_pack(cf) << 32) | revcomp_pack(cf_prev)) >> (2 * (17 - (int)k));
+            const uint32_t rcf = revcomp_pack(cf);
+            const uint32_t rcf_prev = __shfl_up_sync(FULL, rcf, 1);   // (lane 0 emits nothing)
+            const uint64_t R64 = (((uint64_t)rcf << 32) | rcf_prev) >> (2 * (17 - (int)k));
             rlo = (uint32_t)R64; rhi = (uint32_t)(R64 >> 32);
         }
         uint32_t cp[16];   // per window: code (20 bits, k <= 10) | position in the run << 20 (12 bits)
@@ -185,15 +189,15 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
             cp[j] = code;
         }
         if (steady) {
+            if (lane_ok) {   // (lane 0 sits the step out: no select per window)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t sg = lane_ok ? (cp[j] >> p.log2_seg) : trash;
-                cp[j] += atomicAdd(&s_cnt[sg], 1u) << 20;   // (+: one shift-add; the fields do not overlap)
+                for (int j = 0; j < 16; ++j)
+                    cp[j] += atomicAdd(&s_cnt[cp[j] >> log2_seg], 1u) << 20;   // (+: one shift-add; the fields do not overlap)
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const uint32_t sg = (vw & (1u << (15 - j))) ? (cp[j] >> p.log2_seg) : trash;
+                const uint32_t sg = (vw & (1u << (15 - j))) ? (cp[j] >> log2_seg) : trash;
                 cp[j] += atomicAdd(&s_cnt[sg], 1u) << 20;   // (+: one shift-add; the fields do not overlap)
             }
         }
@@ -237,17 +241,18 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 4) bucket_kernel(const BucketPa
         // (an invalid window reads the base of whatever segment its stale code names — harmless — and is redirected)
         const uint32_t trash_slot = BK_TILE_CAP + tid;   // (per thread: no two threads ever store to the same entry)
         if (steady) {
+            if (lane_ok) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t code = cp[j] & 0xFFFFFu;
-                const uint32_t slot = s_base[code >> p.log2_seg] + (cp[j] >> 20);
-                stage[lane_ok ? slot : trash_slot] = (uint16_t)(code & seg_mask);
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t code = cp[j] & 0xFFFFFu;
+                    stage[s_base[code >> log2_seg] + (cp[j] >> 20)] = (uint16_t)(code & seg_mask);
+                }
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const uint32_t code = cp[j] & 0xFFFFFu;
-                const uint32_t slot = s_base[code >> p.log2_seg] + (cp[j] >> 20);
+                const uint32_t slot = s_base[code >> log2_seg] + (cp[j] >> 20);
                 stage[(vw & (1u << (15 - j))) ? slot : trash_slot] = (uint16_t)(code & seg_mask);
             }
         }
