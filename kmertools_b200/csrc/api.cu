@@ -1119,10 +1119,11 @@ int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offs
     const double t0 = now_ms();
     h->stats = ktb_stats{};
     if (n == 0) return KTB_OK;
-    for (uint64_t i = 0; i < n; ++i)
-        if (offsets[i + 1] < offsets[i]) return fail(KTB_ERR_ARG, "offsets must be non-decreasing (at %llu)",
-                                                     (unsigned long long)i);
     if (offsets[n] > offsets[0] && !bases) return fail(KTB_ERR_ARG, "null bases pointer");
+    // The offsets are validated chunk by chunk, right before a chunk is queued: reading 8 bytes per sequence on one
+    // host thread (10 ms for the 10 M reads of the headline config) then runs under the copies of the chunks before it
+    // instead of in front of the whole call.  A chunk's extent must also stay inside [offsets[0], offsets[n]].
+    if (offsets[n] < offsets[0]) return fail(KTB_ERR_ARG, "offsets must be non-decreasing (last < first)");
 
     const uint64_t dim = ktb_oligo_dim(h, canonical);
     const size_t esize = out_dtype == KTB_OUT_F64 ? 8 : 4;
@@ -1172,8 +1173,18 @@ int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offs
     const uint64_t launches_before = 0;
     (void)launches_before;
     uint64_t total_launches = 0;
+    uint64_t checked = 0;   // offsets[0 .. checked] are known to be non-decreasing and <= offsets[n]
+    auto bad_offsets = [&](uint64_t upto) -> int64_t {
+        for (; checked < upto; ++checked)
+            if (offsets[checked + 1] < offsets[checked] || offsets[checked + 1] > offsets[n]) return (int64_t)checked;
+        return -1;
+    };
     for (uint64_t i0 = 0; i0 < n;) {
         uint64_t i1 = std::min(n, i0 + rows_per_chunk);
+        if (const int64_t bad = bad_offsets(i1); bad >= 0) {
+            for (int q = 0; q < NBUF; ++q) drain(q);   // nothing of this call may still be writing into `out`
+            return fail(KTB_ERR_ARG, "offsets must be non-decreasing (at %llu)", (unsigned long long)bad);
+        }
         // cap the bases per chunk (always keep at least one sequence)
         if (offsets[i1] - offsets[i0] > max_chunk_bases && i1 > i0 + 1) {
             const uint64_t *lo = offsets + i0 + 1, *hi = offsets + i1;

@@ -269,6 +269,29 @@ def test_chunked_host_pipeline_matches():
         oc.set_option("chunk_bytes", 512 << 20)
 
 
+def test_bad_offsets_are_rejected_in_any_chunk():
+    """Offsets are validated chunk by chunk (under the copies of the chunks before): a decreasing offset in a LATER
+    chunk must still fail the call, with no copy of this call left in flight, and the handle stays usable."""
+    from kmertools_b200._lib import KtbError, KTB_ERR_ARG
+    rng = np.random.default_rng(17)
+    bases, offsets = random_batch(rng, rng.integers(100, 200, size=20000), noise=0.0)
+    oc = comp(5)
+    oc.set_option("chunk_bytes", 1 << 20)  # ~40 chunks
+    try:
+        for at in (0, 7, 10001, 19999):
+            bad = offsets.copy()
+            if at == 19999:
+                bad[at] = bad[-1] + 1        # beyond the end of the buffer
+            else:
+                bad[at + 1] = bad[at] - 1 if bad[at] else bad[at + 2] + 5   # decreasing
+            with pytest.raises(KtbError) as ei:
+                oc.vectorise_packed(bases, bad, norm_mode=NORM_CLI, mins=True, dtype=np.float32)
+            assert ei.value.code == KTB_ERR_ARG and "non-decreasing" in str(ei.value)
+        check(5, bases, offsets, dtype=np.float32, what="after rejected calls")
+    finally:
+        oc.set_option("chunk_bytes", 512 << 20)
+
+
 def test_chunked_pipeline_with_rejected_groups():
     """Many small chunks whose kernels could overlap on different streams: the short-read kernel's reject list
     and the work counters are shared by the handle, so consecutive chunks must be chained."""
