@@ -116,7 +116,7 @@ struct ktb_oligo {
     uint32_t *d_short_tab_canon = nullptr; // [4^k] (k <= 5): (word byte offset << 22) | 8*(bin&3)
     uint32_t *d_short_tab_raw = nullptr;
     unsigned long long *d_counters = nullptr;  // [4]
-    DevBuf ws_totals, ws_counts, ws_list, ws_list2;
+    DevBuf ws_totals, ws_counts, ws_list, ws_list2, ws_order;
     DevBuf ws_tiles, ws_pool, ws_runs, ws_wavectr;   // bucket path: tile prefix + records, sorted code pool, run descriptors, work counters
     std::vector<cudaEvent_t> wave_ev;      // bucket path: bucket_kernel(w) done
     ChunkSet sets[NBUF];
@@ -138,6 +138,7 @@ struct ktb_oligo {
     int fwd_fold = 1;     // long_kernel MODE_FWD (3 <= k <= 6 canonical, long sequences, u32 / f32 rows)
     int64_t fwd_min_len = 1024;   // mean sequence length from which MODE_FWD replaces seq_kernel mode 1
     int bucket = 1;       // rows larger than shared memory: bucket_kernel + count_kernel instead of global atomics
+    int longest_first = 1;      // long contigs (replica variants of long_kernel): hand out the long sequences first
     int bucket_hist_kb = 64;    // histogram memory of count_kernel per CTA: 64 KB (three CTAs per SM) or 96 KB (two)
     int bucket_wave_ctas = 2;   // bucket_kernel CTAs per SM when the path runs in waves (beside count_kernel's three)
     int bucket_waves = 1;       // waves of that path (bucket_kernel of wave w+1 overlaps count_kernel of wave w); measured: 1 is best
@@ -363,6 +364,22 @@ int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
         if (grid < 1) grid = 1;
         q.grab = h->seq_grab > 0 ? (uint32_t)h->seq_grab
                                  : (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(16, 4096 / std::max<uint64_t>(mean_len, 1)));
+        if (rs && h->longest_first && p.n > grid && p.n < (1ull << 32)) {
+            // more contigs than CTAs: the queue order decides how long the last CTA runs alone (see order_count_kernel)
+            if (int rc = h->ws_order.ensure(p.n * 4 + 129 * 8 + 64)) return rc;
+            OrderParams op{};
+            op.offsets = p.offsets; op.n = p.n; op.list = p.list; op.list_count = p.list_count; op.group_shift = p.group_shift;
+            op.cls = (unsigned long long *)h->ws_order.p;
+            op.order = (uint32_t *)((uint8_t *)h->ws_order.p + 129 * 8 + 56);
+            CU(cudaMemsetAsync(op.cls, 0, 129 * 8, st));
+            const unsigned ogrid = (unsigned)std::min<uint64_t>((nitems + 255) / 256, (uint64_t)h->sm_count * 4);
+            order_count_kernel<<<ogrid, 256, 0, st>>>(op);
+            order_scatter_kernel<<<ogrid, 256, 0, st>>>(op);
+            CU(cudaGetLastError());
+            h->stats.launches += 2;
+            q.list = op.order; q.list_count = op.cls + 128; q.group_shift = 0;
+            q.grab = 1;
+        }
         kern<<<(unsigned)grid, threads, smem, st>>>(q);
         CU(cudaGetLastError());
         h->stats.launches++;
@@ -976,6 +993,7 @@ void ktb_oligo_destroy(ktb_oligo *h) {
     h->ws_counts.release();
     h->ws_list.release();
     h->ws_list2.release();
+    h->ws_order.release();
     h->ws_tiles.release();
     h->ws_pool.release();
     h->ws_runs.release();
@@ -1049,6 +1067,9 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->fwd_min_len = value;
     } else if (!strcmp(key, "bucket")) {
         h->bucket = (int)value;
+    } else if (!strcmp(key, "longest_first")) {
+        if (value < 0 || value > 1) return fail(KTB_ERR_ARG, "longest_first must be 0 or 1");
+        h->longest_first = (int)value;
     } else if (!strcmp(key, "bucket_hist_kb")) {
         if (value != 64 && value != 96) return fail(KTB_ERR_ARG, "bucket_hist_kb must be 64 or 96");
         h->bucket_hist_kb = (int)value;

@@ -210,6 +210,63 @@ __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hby
     }
 }
 
+// ---- longest first.  Contigs of an assembly span orders of magnitude in length, and the work queue hands them out in
+// input order: with a 500 kbp contig drawn near the end, its CTA runs long after the others have drained (20 % of the SM
+// time of a 5,000-contig batch, 5 % at 20,000: profiles/r2_ncu_contigs_summary.txt, sm__cycles_active avg against
+// elapsed).  Two small kernels build the order the queue should use: sequences binned by the log2 of their length, the
+// long classes first (within a class lengths differ by less than 2x, which is all longest-processing-time-first needs).
+struct OrderParams {
+    const uint64_t *offsets;
+    uint64_t n;
+    const uint32_t *list;                  // groups to take (short_kernel's rejects) or nullptr = every sequence
+    const unsigned long long *list_count;
+    uint32_t group_shift;
+    uint32_t *order;                       // out: sequence indices, long classes first
+    unsigned long long *cls;               // [0,64) count per class, [64,128) fill cursor per class, [128] total (zeroed)
+};
+
+__device__ __forceinline__ uint64_t order_items(const OrderParams &p) {
+    return p.list ? ((uint64_t)*p.list_count << p.group_shift) : p.n;
+}
+__device__ __forceinline__ uint64_t order_seq_of(const OrderParams &p, uint64_t item) {
+    if (!p.list) return item;
+    const uint64_t gi = item >> p.group_shift;
+    return ((uint64_t)p.list[gi] << p.group_shift) + (item - (gi << p.group_shift));
+}
+__device__ __forceinline__ uint32_t order_class(const OrderParams &p, uint64_t seq) {
+    return 63u - (uint32_t)__clzll((long long)((p.offsets[seq + 1] - p.offsets[seq]) | 1ull));
+}
+
+__global__ void __launch_bounds__(256) order_count_kernel(const OrderParams p) {
+    __shared__ uint32_t s_cnt[64];
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t nitems = order_items(p);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nitems; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t seq = order_seq_of(p, i);
+        if (seq < p.n) atomicAdd(&s_cnt[order_class(p, seq)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && s_cnt[threadIdx.x]) atomicAdd(p.cls + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) order_scatter_kernel(const OrderParams p) {
+    __shared__ unsigned long long s_base[64];
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int c = 63; c >= 0; --c) { s_base[c] = run; run += p.cls[c]; }
+        if (blockIdx.x == 0) p.cls[128] = run;
+    }
+    __syncthreads();
+    const uint64_t nitems = order_items(p);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nitems; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t seq = order_seq_of(p, i);
+        if (seq >= p.n) continue;
+        const uint32_t c = order_class(p, seq);
+        p.order[s_base[c] + atomicAdd(p.cls + 64 + c, 1ULL)] = (uint32_t)seq;
+    }
+}
+
 // KT: compile-time k of MODE_FWD (0 = p.k); RS: log2 of the lane-private replicas per bin (MODE_FWD, long contigs:
 // k <= 4 has so few bins that the 32 lanes of an atomic keep hitting the same banks — 3.9 wavefronts per ATOMS on
 // config 4 — so bin c of lane l lives at word (c << RS) + (l mod 2^RS): one wavefront per ATOMS, folded at write-out)

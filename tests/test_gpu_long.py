@@ -100,3 +100,19 @@ def test_forward_fold_replicated_bins(k):
     offsets[1:] = np.cumsum([len(s) for s in seqs])
     check(k, bases, offsets, dtype=np.float32, what=f"replicas low complexity k{k}")
     check(k, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"replicas low complexity k{k} counts")
+
+
+@pytest.mark.parametrize("k", [4, 5])
+def test_longest_first_order_for_many_contigs(k):
+    """More long contigs than CTAs: the work queue is re-ordered by length class (order_count_kernel /
+    order_scatter_kernel).  Rows must not depend on the order; short members of the batch ride along."""
+    rng = np.random.default_rng(80 + k)
+    lengths = np.exp(rng.uniform(np.log(2e3), np.log(2.5e5), size=1500)).astype(np.int64)
+    lengths[::97] = rng.integers(0, 200, size=len(lengths[::97]))   # reads short enough for short_kernel's groups
+    lengths[5] = 0
+    bases, offsets = random_batch(rng, lengths, noise=0.002, n_runs=0.5)
+    assert bases.size // len(lengths) >= 32768
+    a = check(k, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"longest first k{k}", longest_first=1)
+    b = check(k, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, what=f"input order k{k}", longest_first=0)
+    assert np.array_equal(a, b)
+    check(k, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, what=f"longest first k{k} f32")

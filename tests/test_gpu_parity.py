@@ -24,7 +24,8 @@ def comp(k):
 OPTION_DEFAULTS = (("force_path", 0), ("packed16", 1), ("even_rank", 1), ("dense_odd", 1),
                    ("wave_persistent", 1), ("wave_smem_rank", 1), ("wave_budget_bytes", 96 << 20),
                    ("global_wave_bytes", 64 << 20), ("k7_mid", 1), ("fwd_fold", 1), ("fwd_min_len", 1024),
-                   ("bucket", 1), ("bucket_log2_seg", 14), ("bucket_waves", 1), ("long_warps", 0), ("fwd_replicas", 1))
+                   ("bucket", 1), ("bucket_log2_seg", 14), ("bucket_waves", 1), ("long_warps", 0), ("fwd_replicas", 1),
+                   ("longest_first", 1), ("bucket_hist_kb", 64))
 
 
 def check(k, bases, offsets, mins=True, norm_mode=NORM_CLI, dtype=np.float32, what="", **opts):
