@@ -259,11 +259,20 @@ __global__ void __launch_bounds__(256) order_scatter_kernel(const OrderParams p)
     }
     __syncthreads();
     const uint64_t nitems = order_items(p);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nitems; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t seq = order_seq_of(p, i);
-        if (seq >= p.n) continue;
-        const uint32_t c = order_class(p, seq);
-        p.order[s_base[c] + atomicAdd(p.cls + 64 + c, 1ULL)] = (uint32_t)seq;
+    const uint32_t lane = threadIdx.x & 31;
+    // whole warps iterate together: the lanes of a class take their slots with ONE atomic (uniform lengths would otherwise
+    // queue every sequence of the batch on one address)
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < nitems; i0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = i0 + lane;
+        const uint64_t seq = i < nitems ? order_seq_of(p, i) : p.n;
+        const bool valid = seq < p.n;
+        const uint32_t c = valid ? order_class(p, seq) : 64u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, c);
+        const uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
+        unsigned long long first = 0;
+        if (valid && lane == leader) first = atomicAdd(p.cls + 64 + c, (unsigned long long)__popc(peers));
+        first = __shfl_sync(0xffffffffu, first, (int)leader);
+        if (valid) p.order[s_base[c] + first + (unsigned long long)__popc(peers & ((1u << lane) - 1u))] = (uint32_t)seq;
     }
 }
 
