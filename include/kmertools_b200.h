@@ -146,6 +146,8 @@ int ktb_oligo_last_stats(const ktb_oligo *h, ktb_stats *out);
  *   "bucket_log2_seg"    log2 of the codes per segment of that path (13 or 14)
  *   "longest_first"      1 (default): batches of long contigs (k <= 5, mean length >= 32 kbp) are handed to the CTAs longest
  *                        length class first; 0: input order
+ *   "bucket_waves"       waves of that path (bucket_kernel of wave w+1 beside count_kernel of wave w; default 1 = off,
+ *                        measured best) and "bucket_wave_ctas" (bucket_kernel CTAs per SM in wave mode, 1..4, default 2)
  *   "bucket_hist_kb"     histogram memory of count_kernel per CTA: 64 (three CTAs per SM) or 96 (two CTAs, more segments
  *                        alternate between two buffers)
  *   "k7_mid"             1: k = 7 rows by long_kernel (middle-base-first keys, scheduled write-out); 0: seq_kernel mode 4
