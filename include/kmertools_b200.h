@@ -120,7 +120,9 @@ int ktb_oligo_vectorise(ktb_oligo *h, const uint8_t *bases, const uint64_t *offs
  * Returns after enqueueing; results are ready when the stream reaches that point.
  * d_bases and d_out must be 16-byte aligned.  The handle owns work counters and scratch buffers, so calls
  * on ONE handle must be ordered with respect to each other (same stream, or event-chained); use one handle
- * per concurrent stream. */
+ * per concurrent stream.  Scratch buffers (reject lists, the pool of the bucket path, the order list of long contigs)
+ * grow with cudaMalloc the first time a larger batch arrives, which synchronises the device once; steady-state calls of
+ * the same or a smaller shape only enqueue. */
 int ktb_oligo_vectorise_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets,
                                uint64_t n, uint64_t total_bases, int canonical, int norm_mode,
                                int out_dtype, void *d_out, uint64_t *d_totals, void *stream);
