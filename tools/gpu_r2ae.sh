@@ -1,0 +1,23 @@
+#!/bin/bash
+# round-2 GPU batch AE: seq_kernel mode 5 (k = 8) write-out with two shared-memory loads in flight; A = previous commit
+mkdir -p gpurun_out
+O=gpurun_out/r2ae
+cp kmertools_b200/lib/libkmertools_b200.so /tmp/libB.so
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scale.py -m gpu -x -q > $O.pytest.txt 2>&1; echo "rc=$?" >> $O.pytest.txt
+tail -3 $O.pytest.txt
+run() { # tag workload scale opts...
+  tag=$1; w=$2; sc=$3; shift 3; flags=""; for kv in "$@"; do flags="$flags --opt $kv"; done
+  timeout 300 python bench.py --workload $w --scale $sc --steps 8 --no-e2e --no-cpu --no-cli --no-per-config $flags 2>&1 | tail -1 | \
+    python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$tag', '$w', '$sc', '$*', 'Gb/s', round(d['value'],1), 'ms', round(d['ms_per_step'],3), 'frac', round(d['roofline']['frac'],3), 'rows1', d['rows_sum_to_one'])"
+}
+{
+for rep in 1 2; do
+cp tools/_probe/libA.so kmertools_b200/lib/libkmertools_b200.so
+run A reads10k_k8 1.0
+run A reads10k_k8 1.0 seq_threads=256
+cp /tmp/libB.so kmertools_b200/lib/libkmertools_b200.so
+run B reads10k_k8 1.0
+run B reads10k_k8 1.0 seq_threads=256
+done
+} > $O.sweep.txt 2>&1
+cat $O.sweep.txt
