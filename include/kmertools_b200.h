@@ -146,6 +146,7 @@ int ktb_oligo_last_stats(const ktb_oligo *h, ktb_stats *out);
  *   "bucket"             1 (default): rows larger than shared memory (canonical k = 9, 10; raw k = 8..10) are built by
  *                        bucket_kernel + count_kernel (partition by code segment, count in shared memory); 0: wave_kernel
  *   "bucket_log2_seg"    log2 of the codes per segment of that path (13 or 14)
+ *   "k8_long"            1 (default): k = 8 u32 / f32 rows are counted by long_kernel MODE_K8; 0: seq_kernel mode 5
  *   "longest_first"      1 (default): batches of long contigs (k <= 5, mean length >= 32 kbp) are handed to the CTAs longest
  *                        length class first; 0: input order
  *   "bucket_waves"       waves of that path (bucket_kernel of wave w+1 beside count_kernel of wave w; default 1 = off,

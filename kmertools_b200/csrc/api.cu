@@ -138,6 +138,7 @@ struct ktb_oligo {
     int fwd_fold = 1;     // long_kernel MODE_FWD (3 <= k <= 6 canonical, long sequences, u32 / f32 rows)
     int64_t fwd_min_len = 1024;   // mean sequence length from which MODE_FWD replaces seq_kernel mode 1
     int bucket = 1;       // rows larger than shared memory: bucket_kernel + count_kernel instead of global atomics
+    int k8_long = 1;            // k = 8 (packed 16-bit rank-space histogram): long_kernel MODE_K8 instead of seq_kernel mode 5
     int longest_first = 1;      // long contigs (replica variants of long_kernel): hand out the long sequences first
     int bucket_hist_kb = 64;    // histogram memory of count_kernel per CTA: 64 KB (three CTAs per SM) or 96 KB (two)
     int bucket_wave_ctas = 2;   // bucket_kernel CTAs per SM when the path runs in waves (beside count_kernel's three)
@@ -332,11 +333,15 @@ int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
         // until the kernel looked ahead across sequences; that needs 72 registers, which 8 warps have and 10 do not
         // (799 against 765 Gbases/s on config 3, 20.6 against 18.6 on 150-base reads).  The small histograms of k <= 5 run
         // best with 4 warps
-        int nw = h->long_warps > 0 ? h->long_warps : (mode == MODE_K7 ? 8 : (mean_len <= 32768 ? 4 : 8));
+        int nw = h->long_warps > 0 ? h->long_warps : (mode == MODE_K7 ? 8 : (mode == MODE_K8 ? (mean_len <= 16384 ? 4 : 8) : (mean_len <= 32768 ? 4 : 8)));
         if (nw == 10 && mode != MODE_K7) nw = 8;
         void (*kern)(const LongParams) = nullptr;
         int rs = 0;
-        if (mode == MODE_K7) {
+        if (mode == MODE_K8) {
+            if (nw != 8) nw = 4;
+            if (nw == 4) kern = nrm ? long_kernel<OUT, true, MODE_K8, 4> : long_kernel<OUT, false, MODE_K8, 4>;
+            else kern = nrm ? long_kernel<OUT, true, MODE_K8, 8> : long_kernel<OUT, false, MODE_K8, 8>;
+        } else if (mode == MODE_K7) {
             if (nw == 4) kern = nrm ? long_kernel<OUT, true, MODE_K7, 4> : long_kernel<OUT, false, MODE_K7, 4>;
             else if (nw == 10) kern = nrm ? long_kernel<OUT, true, MODE_K7, 10> : long_kernel<OUT, false, MODE_K7, 10>;
             else kern = nrm ? long_kernel<OUT, true, MODE_K7, 8> : long_kernel<OUT, false, MODE_K7, 8>;
@@ -352,7 +357,8 @@ int launch_long(ktb_oligo *h, const LongParams &p, int mode, cudaStream_t st) {
         }
         LongParams q = p;
         if (rs) q.hist_words = (((uint32_t)1 << (2 * p.k)) << rs) + (1u << rs);   // + the always-zero replicas (rc slot of palindromes)
-        const size_t smem = ((((size_t)q.hist_words + 31) & ~(size_t)31) + p.dim) * 4;
+        const size_t smem = mode == MODE_K8 ? ((((size_t)q.hist_words + 3) & ~(size_t)3) * 4 + (size_t)p.even_words * 5 + 16)
+                                            : ((((size_t)q.hist_words + 31) & ~(size_t)31) + p.dim) * 4;
         if (int rc = set_smem(kern, smem)) return rc;
         int per_sm = 1;
         const int threads = nw * 32;
@@ -476,7 +482,20 @@ int run_device(ktb_oligo *h, const uint8_t *d_bases, const uint64_t *d_offsets, 
             // redone with 32-bit counters (mode 7) in a second launch
             if (int rc = h->ws_list2.ensure(n * 4)) return rc;
             qp.out_list = (uint32_t *)h->ws_list2.p; qp.out_count = h->d_counters + 3;
-            if (int rc = launch_seq<OUT>(h, qp, 5, st)) return rc;
+            if (OUT != OUT_F64 && h->k8_long && h->k == 8 && canonical && h->force_path != 3) {
+                // same arithmetic inside long_kernel's loop (look-back lane, look-ahead across sequences)
+                LongParams lp{};
+                lp.bases = d_bases; lp.offsets = d_offsets; lp.n = n; lp.total_bases = total_bases;
+                lp.out = d_out; lp.totals = d_totals;
+                lp.even_tab = h->d_even_tab; lp.even_words = h->even_words;
+                lp.out_list = qp.out_list; lp.out_count = qp.out_count;
+                lp.counter = h->d_counters + 1;
+                lp.list = qp.list; lp.list_count = qp.list_count;
+                lp.group_shift = 4;   // SHORT_G
+                lp.k = h->k; lp.dim = (uint32_t)dim; lp.hist_words = (uint32_t)hist_entries;
+                lp.norm_mode = norm_mode; lp.canonical = canonical;
+                if (int rc = launch_long<OUT>(h, lp, MODE_K8, st)) return rc;
+            } else if (int rc = launch_seq<OUT>(h, qp, 5, st)) return rc;
             SeqParams q2 = qp;
             q2.hist_entries = (uint32_t)h->dim_canon;
             q2.counter = h->d_counters + 0;   // unused by the short kernel for this k, zeroed above
@@ -1067,6 +1086,9 @@ int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value) {
         h->fwd_min_len = value;
     } else if (!strcmp(key, "bucket")) {
         h->bucket = (int)value;
+    } else if (!strcmp(key, "k8_long")) {
+        if (value < 0 || value > 1) return fail(KTB_ERR_ARG, "k8_long must be 0 or 1");
+        h->k8_long = (int)value;
     } else if (!strcmp(key, "longest_first")) {
         if (value < 0 || value > 1) return fail(KTB_ERR_ARG, "longest_first must be 0 or 1");
         h->longest_first = (int)value;

@@ -27,13 +27,18 @@
 //            strands at write-out, row[rank(c)] = hist[c] + hist[rc(c)] (once per column instead of once per
 //            k-mer): no reverse-complement packing, no second extraction and no min in the inner loop.
 //
-// Both write rows as one bulk copy from shared memory.  f64 output keeps seq_kernel.
+//   MODE_K8  (even k whose packed rank-space histogram fits shared memory: k = 8).  seq_kernel mode 5's arithmetic — rank from
+//            two small shared-memory tables, 16-bit counters packed two to a word, linear unpacking sweep with plain
+//            stores (the row, 128.5 KB, does not fit beside the histogram) — inside this kernel's loop: look-back lane
+//            instead of a priming chunk, look-ahead across sequences.
+//
+// MODE_K7 and MODE_FWD write rows as one bulk copy from shared memory.  f64 output keeps seq_kernel.
 #pragma once
 #include "kernels.cuh"
 
 namespace ktb {
 
-constexpr int MODE_K7 = 0, MODE_FWD = 1;
+constexpr int MODE_K7 = 0, MODE_FWD = 1, MODE_K8 = 2;
 constexpr int LONG_WARPS = 8;
 constexpr uint32_t K7_BINS = 8192;
 constexpr uint32_t FLOAT_2P23 = 0x4B000000u;
@@ -47,6 +52,10 @@ struct LongParams {
     uint64_t *totals;            // optional
     const uint32_t *sched;       // MODE_K7: [dim] (bin byte offset | rank byte offset << 16), group-major (see api.cu)
                                  // MODE_FWD: [dim] (byte offset of c | byte offset of rc(c) << 16) in rank order
+    const uint32_t *even_tab;    // MODE_K8: [even_words] bitmap words then u16 prefixes (seq_kernel mode 5 / 7 tables, api.cu)
+    uint32_t even_words;
+    uint32_t *out_list;          // MODE_K8: sequences with more than 65535 windows are appended here (second launch)
+    unsigned long long *out_count;
     unsigned long long *counter; // dynamic work counter (zeroed before launch)
     const uint32_t *list;        // groups to process (short_kernel's rejects); nullptr = every group
     const unsigned long long *list_count;
@@ -121,7 +130,7 @@ struct K7Sched {
 
 template <int OUT, bool NORM, int MODE, int NW, bool SMALL, int RS>
 __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hbytes, uint32_t *stage, uint64_t dv,
-                                               const K7Sched &ks) {
+                                               const K7Sched &ks, uint64_t row_seq) {
     using T = typename OutT<OUT>::type;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float dF = (float)dv;
@@ -177,6 +186,31 @@ __device__ __forceinline__ void long_write_row(const LongParams &p, uint8_t *hby
             if (w + NW < niter) {
                 move4(B);
                 if (w + 3 * NW < niter) B = __ldg(sched4 + (w + 3 * NW) * 32);
+            }
+        }
+    } else if constexpr (MODE == MODE_K8) {
+        // rank space, 16-bit counters packed two to a word (rank r -> word r/2, half r&1): linear sweep, one 128-bit shared
+        // load = 8 counts = two 128-bit stores; zeroed on the way.  dim % 8 == 0 (checked on the host).
+        (void)ks; (void)stage;
+        uint32_t *hist = reinterpret_cast<uint32_t *>(hbytes);
+        T *row = reinterpret_cast<T *>(p.out) + row_seq * (uint64_t)p.dim;
+        for (uint32_t w = tid * 4u; w < p.hist_words; w += NW * 32 * 4u) {
+            const uint4 hv = *reinterpret_cast<const uint4 *>(hist + w);
+            *reinterpret_cast<uint4 *>(hist + w) = make_uint4(0, 0, 0, 0);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+            T e[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                e[2 * q] = cvt_count<OUT, NORM, SMALL>(hw[q] & 0xFFFFu, dF, rinv, dD);
+                e[2 * q + 1] = cvt_count<OUT, NORM, SMALL>(hw[q] >> 16, dF, rinv, dD);
+            }
+            T *dst = row + 2u * w;
+            if constexpr (OUT == OUT_F32) {
+                reinterpret_cast<float4 *>(dst)[0] = make_float4(e[0], e[1], e[2], e[3]);
+                reinterpret_cast<float4 *>(dst)[1] = make_float4(e[4], e[5], e[6], e[7]);
+            } else {
+                reinterpret_cast<uint4 *>(dst)[0] = make_uint4(e[0], e[1], e[2], e[3]);
+                reinterpret_cast<uint4 *>(dst)[1] = make_uint4(e[4], e[5], e[6], e[7]);
             }
         }
     } else if constexpr (RS == 0) {
@@ -280,7 +314,7 @@ __global__ void __launch_bounds__(256) order_scatter_kernel(const OrderParams p)
 // k <= 4 has so few bins that the 32 lanes of an atomic keep hitting the same banks — 3.9 wavefronts per ATOMS on
 // config 4 — so bin c of lane l lives at word (c << RS) + (l mod 2^RS): one wavefront per ATOMS, folded at write-out)
 template <int OUT, bool NORM, int MODE, int NW, int KT = 0, int RS = 0>
-__global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 8)) long_kernel(const LongParams p) {
+__global__ void __launch_bounds__(NW * 32, (MODE == MODE_K7 || MODE == MODE_K8) ? 3 : (NW >= 8 ? 4 : 8)) long_kernel(const LongParams p) {
     static_assert(OUT == OUT_U32 || OUT == OUT_F32, "f64 rows keep seq_kernel");
     static_assert(NW == 4 || NW == 8 || NW == 10, "warps per CTA");
     extern __shared__ __align__(128) uint32_t lsm[];
@@ -303,10 +337,19 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
     const uint64_t nitems = ngroups << gshift;
     if ((uint64_t)blockIdx.x >= nitems) return;
     for (uint32_t i = tid; i < p.hist_words; i += NW * 32) hist[i] = INIT;
+    // MODE_K8: rank tables behind the histogram (bitmap words, then every second u16 prefix: seq_kernel mode 5's layout)
+    uint32_t *s_bitmap = hist + ((p.hist_words + 3u) & ~3u);
+    uint16_t *s_prefix = reinterpret_cast<uint16_t *>(s_bitmap + p.even_words);
+    if constexpr (MODE == MODE_K8) {
+        for (uint32_t i = tid; i < p.even_words; i += NW * 32) s_bitmap[i] = __ldg(p.even_tab + i);
+        const uint16_t *gp = reinterpret_cast<const uint16_t *>(p.even_tab + p.even_words);
+        for (uint32_t i = tid; i < p.even_words / 2; i += NW * 32) s_prefix[i] = gp[2 * i];
+    }
+    (void)s_bitmap; (void)s_prefix;
     if (tid == 0) { s_total[0] = 0; s_total[1] = 0; }
     __syncthreads();
 
-    const uint32_t k = (MODE == MODE_K7) ? 7u : (KT ? (uint32_t)KT : p.k);
+    const uint32_t k = (MODE == MODE_K7) ? 7u : (MODE == MODE_K8) ? 8u : (KT ? (uint32_t)KT : p.k);
     const uint32_t kmaskR = ((1u << (2 * k)) - 1u) << (2 + RS);            // code pre-scaled to the byte offset of its bin
     const uint32_t lane_off = ((uint32_t)lane & ((1u << RS) - 1u)) << 2;   // this lane's replica
     (void)kmaskR; (void)lane_off;
@@ -403,7 +446,7 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
     // Only k = 7 looks ahead.  The small histograms of k <= 5 run 4 - 8 CTAs per SM, which hide those latencies already
     // (measured with look-ahead: -3 % on 10 kbp reads at k = 5), and a CTA that reserves two 500 kbp contigs in advance
     // lengthens the tail of the launch (-5 % on config 4).
-    constexpr bool LA = (MODE == MODE_K7);
+    constexpr bool LA = (MODE == MODE_K7 || MODE == MODE_K8);
     // prologue: the first two items, with their latencies exposed once per CTA
     la_ticket(); la_resolve(0);
     if constexpr (LA) { la_ticket(); la_resolve(1); }
@@ -428,9 +471,12 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
 
     while (seq != ITEM_DONE) {
         if constexpr (LA) la_ticket();
-        const bool real = seq != ITEM_SKIP;   // uniform for the CTA
+        // MODE_K8: 16-bit counters — a sequence that could hold more than 65535 windows goes to the second launch (out_list)
+        const bool over = MODE == MODE_K8 && pl.nch >= 4096u;
+        const bool real = seq != ITEM_SKIP && !over;   // uniform for the CTA
+        if (over && tid == 0) p.out_list[atomicAdd(p.out_count, 1ULL)] = (uint32_t)seq;
         uint32_t mine = 0;
-        if (pl.w0 < pl.w1) {
+        if (pl.w0 < pl.w1 && !over) {
             const uint32_t nch = pl.nch, w0 = pl.w0, w1 = pl.w1;
             const bool lookback = pl.flags & 1u;
             uint32_t carry_cf = 0, carry_vm = 0;
@@ -458,6 +504,22 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
                     k7_keys_phase<1>(cf, cf_prev, rc, rc_prev, off);
                     k7_keys_phase<2>(cf, cf_prev, rc, rc_prev, off);
                     k7_keys_phase<3>(cf, cf_prev, rc, rc_prev, off);
+                } else if constexpr (MODE == MODE_K8) {
+                    // canonical code, then its rank from the two shared-memory tables (seq_kernel mode 5): off[e] = rank
+                    const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
+                    const uint64_t R64 = ((((uint64_t)revcomp_pack(cf)) << 32) | revcomp_pack(cf_prev)) >> (2 * (17 - 8));
+                    constexpr uint32_t kmask8 = 0xFFFFu;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const uint32_t f = (e < 15 ? (uint32_t)(F64 >> (2 * (15 - e))) : cf) & kmask8;
+                        const uint32_t r = (uint32_t)(R64 >> (2 * e)) & kmask8;
+                        const uint32_t c = min(f, r);
+                        const uint32_t w = c >> 5;
+                        const uint2 bw = reinterpret_cast<const uint2 *>(s_bitmap)[w >> 1];   // words w & ~1, w | 1
+                        const bool odd = (w & 1u) != 0u;
+                        const uint32_t below = (odd ? bw.y : bw.x) & ((1u << (c & 31u)) - 1u);
+                        off[e] = (uint32_t)s_prefix[w >> 1] + (uint32_t)__popc(below) + (odd ? (uint32_t)__popc(bw.x) : 0u);
+                    }
                 } else {
                     const uint64_t F64 = ((uint64_t)cf_prev << 32) | cf;
 #pragma unroll
@@ -468,17 +530,21 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
                         off[e] = (x & kmaskR) | lane_off;
                     }
                 }
+                // (MODE_K8: off[e] is a rank; its 16-bit counter is half (rank & 1) of word rank / 2)
+                auto bump = [&](const uint32_t o, const uint32_t inc) {
+                    if constexpr (MODE == MODE_K8) atomicAdd(hist + (o >> 1), inc << ((o & 1u) << 4));
+                    else atomicAdd(reinterpret_cast<uint32_t *>(hbytes + o), inc);
+                };
                 if (__all_sync(FULL, vw == 0xFFFFu)) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), 1u);
+                    for (int e = 0; e < 16; ++e) bump(off[e], 1u);
                 } else if (__all_sync(FULL, silent || vw == 0xFFFFu)) {   // full step behind a look-back lane
                     const uint32_t inc = silent ? 0u : 1u;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), inc);
+                    for (int e = 0; e < 16; ++e) bump(off[e], inc);
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e)   // branch-free: an invalid window adds 0
-                        atomicAdd(reinterpret_cast<uint32_t *>(hbytes + off[e]), (vw >> (15 - e)) & 1u);
+                    for (int e = 0; e < 16; ++e) bump(off[e], (vw >> (15 - e)) & 1u);   // branch-free: an invalid window adds 0
                 }
             };
             for (uint32_t c0 = w0; c0 < w1; c0 += 64) {
@@ -502,21 +568,21 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
             K7Sched ks;
             if constexpr (MODE == MODE_K7) ks.template load_nw<NW>(p.sched, warp, lane);
             // the row image is about to be overwritten: the bulk copy of the previous row must have read it
-            if (tid == 0) bulk_wait_read();
+            if constexpr (MODE != MODE_K8) { if (tid == 0) bulk_wait_read(); }
             __syncthreads();
             const uint32_t total = s_total[it & 1];
             if (tid == 0) s_total[(it + 1) & 1] = 0;
             ++it;
             const uint64_t dv = norm_divisor(total, p.norm_mode, p.canonical);
             if (tid == 0 && p.totals) p.totals[seq] = total;
-            if (dv < (1ULL << 23)) long_write_row<OUT, NORM, MODE, NW, true, RS>(p, hbytes, stage, dv, ks);
-            else long_write_row<OUT, NORM, MODE, NW, false, RS>(p, hbytes, stage, dv, ks);
-            fence_async_smem();
+            if (dv < (1ULL << 23)) long_write_row<OUT, NORM, MODE, NW, true, RS>(p, hbytes, stage, dv, ks, seq);
+            else long_write_row<OUT, NORM, MODE, NW, false, RS>(p, hbytes, stage, dv, ks, seq);
+            if constexpr (MODE != MODE_K8) fence_async_smem();
         }
         if constexpr (!LA) { la_ticket(); la_resolve(slot); }   // (slot 1 <-> 2: not the one the current item was read from)
         la_arrived();
         __syncthreads();
-        if (real && tid == 0) bulk_store(out + seq * (uint64_t)p.dim, stage, p.dim * 4u);
+        if constexpr (MODE != MODE_K8) { if (real && tid == 0) bulk_store(out + seq * (uint64_t)p.dim, stage, p.dim * 4u); }
         seq = s_nx[slot][0];
         {
             const unsigned long long s0 = s_nx[slot][1], s1 = s_nx[slot][2];
@@ -530,7 +596,7 @@ __global__ void __launch_bounds__(NW * 32, MODE == MODE_K7 ? 3 : (NW >= 8 ? 4 : 
             buf_b = fetch(pl, pl.w0 + 32 + lane);
         }
     }
-    if (tid == 0) bulk_wait_all();
+    if constexpr (MODE != MODE_K8) { if (tid == 0) bulk_wait_all(); }
 }
 
 }  // namespace ktb

@@ -25,7 +25,7 @@ OPTION_DEFAULTS = (("force_path", 0), ("packed16", 1), ("even_rank", 1), ("dense
                    ("wave_persistent", 1), ("wave_smem_rank", 1), ("wave_budget_bytes", 96 << 20),
                    ("global_wave_bytes", 64 << 20), ("k7_mid", 1), ("fwd_fold", 1), ("fwd_min_len", 1024),
                    ("bucket", 1), ("bucket_log2_seg", 14), ("bucket_waves", 1), ("long_warps", 0), ("fwd_replicas", 1),
-                   ("longest_first", 1), ("bucket_hist_kb", 64))
+                   ("longest_first", 1), ("bucket_hist_kb", 64), ("k8_long", 1))
 
 
 def check(k, bases, offsets, mins=True, norm_mode=NORM_CLI, dtype=np.float32, what="", **opts):
@@ -167,6 +167,26 @@ def test_k8_packed16_variant_with_overflow_fallback():
     check(8, bases, offsets, norm_mode=NORM_COUNTS, dtype=np.uint32, packed16=1, what="k8 packed counts")
     check(8, bases, offsets, norm_mode=NORM_CLI, dtype=np.float32, packed16=1, what="k8 packed f32")
     check(8, bases, offsets, norm_mode=NORM_CLI, dtype=np.float64, packed16=1, what="k8 packed f64")
+    # the same arithmetic in both hosts of it: long_kernel MODE_K8 (default) and seq_kernel mode 5
+    for dtype, norm in ((np.uint32, NORM_COUNTS), (np.float32, NORM_CLI), (np.float32, NORM_PY)):
+        for warps in (0, 4, 8):
+            a = check(8, bases, offsets, norm_mode=norm, dtype=dtype, what=f"k8 long_kernel w{warps}", k8_long=1, long_warps=warps)
+            b = check(8, bases, offsets, norm_mode=norm, dtype=dtype, what="k8 seq_kernel", k8_long=0)
+            assert np.array_equal(a, b)
+
+
+def test_k8_long_kernel_mixed_lengths():
+    """MODE_K8 across step / warp boundaries, short reads that ride along, empty and sub-k sequences, Ns, unaligned
+    starts; many sequences so that the look-ahead ring wraps."""
+    rng = np.random.default_rng(89)
+    lengths = np.r_[np.arange(0, 40), [511, 512, 513, 527, 528, 1000, 4096, 4111, 4112, 10_000, 16_384, 16_385, 33_000],
+                    rng.integers(100, 3000, size=400), rng.integers(5000, 12000, size=60)]
+    rng.shuffle(lengths)
+    bases, offsets = random_batch(rng, lengths, noise=0.004, n_runs=0.2)
+    for dtype, norm in ((np.uint32, NORM_COUNTS), (np.float32, NORM_CLI)):
+        a = check(8, bases, offsets, norm_mode=norm, dtype=dtype, what="k8 mixed long_kernel", k8_long=1)
+        b = check(8, bases, offsets, norm_mode=norm, dtype=dtype, what="k8 mixed seq_kernel", k8_long=0)
+        assert np.array_equal(a, b)
 
 
 def test_alternative_histogram_modes_agree():
