@@ -1,7 +1,7 @@
 // long_kernel.cuh — CTA-per-sequence kernel for medium / long sequences, second generation (round 2).
 //
 // Same arithmetic as seq_kernel (kernels.cuh; closed form of kmer/src/kmer.rs:80-106 +
-// composition/src/oligo.rs:231-259), with two changes that remove most of the per-k-mer and per-column work:
+// composition/src/oligo.rs:231-259).  Three modes; the first two remove most of the per-k-mer and per-column work:
 //
 //   MODE_K7  (k = 7, canonical).  The two strands of an odd k-mer differ in the top bit of their MIDDLE base
 //            (m vs 3-m), so a 16-bit key whose most significant digit is the middle base orders the strands:
@@ -23,16 +23,18 @@
 //            Bins hold the FLOAT 2^23 + count (initial value 0x4B000000, incremented with integer atomics), so
 //            the count -> float conversion of the normalisation is free.
 //
-//   MODE_FWD (3 <= k <= 6, canonical, long sequences).  Counts the FORWARD code only (4^k bins) and folds the two
+//   MODE_FWD (3 <= k <= 5, canonical, long sequences).  Counts the FORWARD code only (4^k bins) and folds the two
 //            strands at write-out, row[rank(c)] = hist[c] + hist[rc(c)] (once per column instead of once per
-//            k-mer): no reverse-complement packing, no second extraction and no min in the inner loop.
+//            k-mer): no reverse-complement packing, no second extraction and no min in the inner loop.  Long contigs
+//            count into lane-private replicas of the bins (RS) and are handed out longest length class first.
 //
 //   MODE_K8  (even k whose packed rank-space histogram fits shared memory: k = 8).  seq_kernel mode 5's arithmetic — rank from
 //            two small shared-memory tables, 16-bit counters packed two to a word, linear unpacking sweep with plain
 //            stores (the row, 128.5 KB, does not fit beside the histogram) — inside this kernel's loop: look-back lane
 //            instead of a priming chunk, look-ahead across sequences.
 //
-// MODE_K7 and MODE_FWD write rows as one bulk copy from shared memory.  f64 output keeps seq_kernel.
+// MODE_K7 and MODE_FWD write rows as one bulk copy from shared memory.  MODE_K7 and MODE_K8 look two sequences ahead
+// (work ticket, offsets by cp.async, first bases before the write-out).  f64 output keeps seq_kernel.
 #pragma once
 #include "kernels.cuh"
 
