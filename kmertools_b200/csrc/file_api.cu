@@ -358,15 +358,15 @@ static int run_file(const ktb_file_opts *o, ktb_file_stats *stats, int cgr_vecsi
     const uint64_t dim = ktb_oligo_dim(h, cgr ? 1 : o->canonical);
 
     // `-t` (kmertools/src/args.rs:249-251; 0 = all cores): threads of the output writer and of the host formatter
-    // (all cores = the CPUs this process may run on; the mapping writer on tmpfs gains with every thread up to 16 —
-    // page faults of a fresh shared mapping, ~0.6 GB/s per thread — while write() on a disk file system uses one)
+    // (all cores = the CPUs this process may run on, at most 8: sixteen writer threads measured no faster on tmpfs —
+    // 149 against 145 ms per GB, profiles/r2_cli_writer.txt — and write() on a disk file system uses one anyway)
     int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     {
         cpu_set_t set;
         CPU_ZERO(&set);
         if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = CPU_COUNT(&set);
     }
-    const int nthreads = o->threads > 0 ? std::min(o->threads, 64) : std::min(hw, 16);
+    const int nthreads = o->threads > 0 ? std::min(o->threads, 64) : std::min(hw, 8);
     ktb::SpanWriter wr;
     if (!wr.open(o->out_path, nthreads, &err)) return ktb_internal_fail(KTB_ERR_IO, err.c_str());
     ktb::SpanWriter::Ticket header_ticket;
