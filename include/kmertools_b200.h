@@ -136,27 +136,33 @@ int ktb_oligo_last_stats(const ktb_oligo *h, ktb_stats *out);
  *   "force_path"         0 auto, 1 flat-decomposition global-atomic kernel only, 2 no short-read kernel
  *   "seq_threads"        CTA size of the CTA-per-sequence kernel (0 = heuristic)
  *   "seq_grab"           sequences a CTA of that kernel takes per trip to the work counter (0 = heuristic)
- *   "dense_odd"          1 (default): dense middle-base histogram for k = 7, 0: code-space histogram
- *   "packed16"           1: packed 16-bit code-space histogram for k = 8 (default 0: rank-space histogram)
- *   "wave_persistent"    1 (default): histograms larger than shared memory (k >= 9, raw k >= 8) are counted by one
- *                        cooperative launch for u32 / f32 output; 0: one memset + kernel (+ normalise) per wave
+ *   "dense_odd"          1 (default): dense middle-base histogram for k = 7 in seq_kernel (mode 4), 0: code-space histogram
+ *   "even_rank"          1 (default): even k whose rank-space histogram fits shared memory (k = 8) compute the rank from two
+ *                        small shared-memory tables (seq_kernel mode 7 / 5, long_kernel MODE_K8); 0: rank table in L2 (mode 2)
+ *   "packed16"           1 (default): 16-bit counters packed two to a word for k = 8 (three CTAs per SM; sequences with more
+ *                        than 65535 windows take a second launch with 32-bit counters); 0: 32-bit rank-space histogram
+ *   "k8_long"            1 (default): k = 8 u32 / f32 rows are counted by long_kernel MODE_K8; 0: seq_kernel mode 5
+ *   "k7_mid"             1 (default): k = 7 rows by long_kernel (middle-base-first keys, scheduled write-out); 0: seq_kernel
+ *   "fwd_fold"           1 (default): 3 <= k <= 5 rows of long sequences by long_kernel (forward codes folded at write-out)
+ *   "fwd_min_len"        mean sequence length from which "fwd_fold" applies (default 1024)
+ *   "fwd_replicas"       1 (default): long contigs (mean length >= 32 kbp) at k <= 5 count into lane-private replicas of the bins
+ *   "longest_first"      1 (default): such batches of long contigs are handed to the CTAs longest length class first;
+ *                        0: input order
+ *   "long_warps"         warps per CTA of long_kernel (0 = heuristic; 4, 8 or 10)
+ *   "bucket"             1 (default): rows larger than shared memory (canonical k = 9, 10; raw k = 8..10) are built by
+ *                        bucket_kernel + count_kernel (partition by code segment, count in shared memory); 0: wave_kernel
+ *   "bucket_log2_seg"    log2 of the codes per segment of that path (13 or 14, default 14)
+ *   "bucket_hist_kb"     histogram memory of count_kernel per CTA: 64 (default, three CTAs per SM) or 96 (two CTAs, more
+ *                        segments alternate between two buffers)
+ *   "bucket_waves"       waves of that path (bucket_kernel of wave w+1 beside count_kernel of wave w; default 1 = off,
+ *                        measured best) and "bucket_wave_ctas" (bucket_kernel CTAs per SM in wave mode, 1..4, default 2)
+ *   "wave_persistent"    1 (default): where the bucket path does not apply (k >= 11, or "bucket" = 0) histograms larger than
+ *                        shared memory are counted by one cooperative launch for u32 / f32 output; 0: one memset + kernel
+ *                        (+ normalise) per wave
  *   "wave_smem_rank"     1 (default): that kernel computes canonical ranks from shared-memory tables (k <= 10)
  *   "wave_budget_bytes"  L2 budget of that kernel; a wave (rows zeroed, counted and normalised together) is a third of it
  *   "global_wave_bytes"  bytes of output rows zeroed + counted together by the multi-launch variant (fits L2)
- *   "bucket"             1 (default): rows larger than shared memory (canonical k = 9, 10; raw k = 8..10) are built by
- *                        bucket_kernel + count_kernel (partition by code segment, count in shared memory); 0: wave_kernel
- *   "bucket_log2_seg"    log2 of the codes per segment of that path (13 or 14)
- *   "k8_long"            1 (default): k = 8 u32 / f32 rows are counted by long_kernel MODE_K8; 0: seq_kernel mode 5
- *   "longest_first"      1 (default): batches of long contigs (k <= 5, mean length >= 32 kbp) are handed to the CTAs longest
- *                        length class first; 0: input order
- *   "bucket_waves"       waves of that path (bucket_kernel of wave w+1 beside count_kernel of wave w; default 1 = off,
- *                        measured best) and "bucket_wave_ctas" (bucket_kernel CTAs per SM in wave mode, 1..4, default 2)
- *   "bucket_hist_kb"     histogram memory of count_kernel per CTA: 64 (three CTAs per SM) or 96 (two CTAs, more segments
- *                        alternate between two buffers)
- *   "k7_mid"             1: k = 7 rows by long_kernel (middle-base-first keys, scheduled write-out); 0: seq_kernel mode 4
- *   "fwd_fold"           1 (default): 3 <= k <= 5 rows of long sequences by long_kernel (forward codes folded at write-out)
- *   "fwd_min_len"        mean sequence length from which "fwd_fold" applies
- *   "long_warps"         warps per CTA of long_kernel (0 = heuristic, 4 or 8) */
+ *   "global_steps_per_warp"  granularity of that variant's work items: steps of 512 bases per warp (default 1) */
 int ktb_oligo_set_option(ktb_oligo *h, const char *key, int64_t value);
 
 /* Pinned host memory for callers that want asynchronous copies (usable from every device).  ktb_host_alloc_near binds

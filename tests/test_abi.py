@@ -80,3 +80,21 @@ def test_utils_mirror():  # tests/test_utils.py of the reference
     assert utils.to_numeric("T" * 32) == (2 ** 64 - 1, 0)
     with pytest.raises(ValueError, match="Invalid k-mer length: 33, must be <= 32"):   # pybindings/src/kmer.rs:57-63
         utils.to_numeric("A" * 33)
+
+
+def test_documented_options_are_the_accepted_options():
+    """Every option named in the header's ktb_oligo_set_option comment is handled in csrc/api.cu and vice versa, so the
+    documentation of the tuning knobs cannot drift from the code."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    header = (root / "include" / "kmertools_b200.h").read_text()
+    block = header[:header.index("int ktb_oligo_set_option(")]
+    block = block[block.rindex("/*"):]
+    documented = set(re.findall(r'^ \*\s+"([a-z0-9_]+)"', block, flags=re.M)) | set(re.findall(r'and "([a-z0-9_]+)"', block))
+    api = (root / "kmertools_b200" / "csrc" / "api.cu").read_text()
+    body = api[api.index("int ktb_oligo_set_option("):]
+    body = body[:body.index("\n}\n")]
+    accepted = set(re.findall(r'strcmp\(key, "([a-z0-9_]+)"\)', body))
+    assert accepted, "no options found in api.cu"
+    assert documented == accepted, f"undocumented: {sorted(accepted - documented)}; unknown to the code: {sorted(documented - accepted)}"
